@@ -1,0 +1,156 @@
+/*
+ * ebm_b200.h -- C ABI of the B200-native MCMC negative-sampling hot path.
+ *
+ * Drop-in boundary for torchebm's sampler inner loops (reference = soran-ghaderi/torchebm @ a77aeee,
+ * paths relative to its root).  All entry points:
+ *   - take plain pointers and sizes (no torch types); `*_dev` / unmarked pointers are DEVICE pointers,
+ *     `const double* ..._host` are HOST arrays that are consumed before the call returns;
+ *   - are asynchronous on `stream` (a cudaStream_t passed as void*), allocate nothing, keep no state
+ *     besides a per-device property cache, and are safe to call concurrently on different streams;
+ *   - return 0 on success, a positive cudaError_t, or a negative EBM_ERR_* code.  `ebm_last_error()`
+ *     returns a thread-local description of the last failure.
+ * State is fp32, row-major contiguous [n, dim].
+ */
+#ifndef EBM_B200_H
+#define EBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EBM_ABI_VERSION 1
+
+#define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
+#define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
+
+/* Energy kinds: torchebm/core/base_model.py (DoubleWell :130-148, Gaussian :151-210, Harmonic :213-229,
+ * Rastrigin :297-316); MLP = user Sequential(Linear, act, Linear, act, Linear(.,1)) energies
+ * (examples/20-training/01-mcmc-losses/01-cd-k/main.py:20-30); MoG is not in the reference (north_star). */
+enum {
+  EBM_ENERGY_DOUBLE_WELL = 0,
+  EBM_ENERGY_HARMONIC    = 1,
+  EBM_ENERGY_RASTRIGIN   = 2,
+  EBM_ENERGY_GAUSSIAN    = 3,
+  EBM_ENERGY_MOG         = 4,
+  EBM_ENERGY_MLP         = 5
+};
+
+enum { EBM_ACT_SILU = 0, EBM_ACT_TANH = 1, EBM_ACT_RELU = 2, EBM_ACT_SOFTPLUS = 3 };
+
+/* Where the Gaussian noise / uniforms come from.
+ *   INJECTED: read from caller-provided device arrays (parity with the CPU oracle).
+ *   TORCH   : Philox4x32-10 laid out exactly like torch's CUDA `randn_like` / `normal_` / `rand`
+ *             (ATen/native/cuda/DistributionTemplates.h:50-91), so a burst consumes the generator
+ *             stream the reference sampler would: same seed + offset => same chains.
+ *   NATIVE  : Philox4x32-10, one block per aligned quad of consecutive elements (cheapest). */
+enum { EBM_RNG_INJECTED = 0, EBM_RNG_TORCH = 1, EBM_RNG_NATIVE = 2 };
+
+enum { EBM_MASS_NONE = 0, EBM_MASS_SCALAR = 1, EBM_MASS_VECTOR = 2 };
+
+typedef struct EbmEnergyDesc {
+  int32_t kind;         /* EBM_ENERGY_* */
+  int32_t dim;          /* D */
+  int32_t n_components; /* MoG: K */
+  int32_t hidden1;      /* MLP: H1 */
+  int32_t hidden2;      /* MLP: H2 */
+  int32_t activation;   /* MLP: EBM_ACT_* */
+  /* scalar parameters (fp32, already rounded the way torch rounds the Python doubles):
+   *   DoubleWell: p[0] = barrier_height, p[1] = b*b
+   *   Harmonic  : p[0] = 0.5*k
+   *   Rastrigin : p[0] = a, p[1] = 2*pi, p[2] = a*D                                  */
+  float p[4];
+  /* device buffers:
+   *   Gaussian: buf[0] = mean[D], buf[1] = cov_inv[D,D]
+   *   MoG     : buf[0] = means[K,D], buf[1] = sigmas[K], buf[2] = weights[K]
+   *   MLP     : buf[0] = W1[H1,D], buf[1] = b1[H1], buf[2] = W2[H2,H1], buf[3] = b2[H2],
+   *             buf[4] = w3[H2], buf[5] = b3[1]            (torch [out,in] layout)   */
+  const float* buf[8];
+} EbmEnergyDesc;
+
+int         ebm_abi_version(void);
+const char* ebm_last_error(void);
+
+/* Number of SMs and T = 256 * min(SMs * maxThreadsPerSM/256, ceil(numel/256)) of torch's distribution
+ * kernels on `device`; the generator offset a torch-layout draw of `numel` elements consumes. */
+int     ebm_device_sm_count(int device);
+int64_t ebm_torch_rng_threads(int device, int64_t numel);
+int64_t ebm_torch_rng_offset_increment(int device, int64_t numel);
+
+/* E(x) -> energy[n]; replaces `model(x)` (BaseModel.forward, base_model.py:49-60). */
+int ebm_energy_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, void* stream);
+
+/* grad_x E(x) -> grad[n, dim]; replaces `BaseModel.gradient` (base_model.py:62-127). */
+int ebm_gradient_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* grad, void* stream);
+
+/* One Euler-Maruyama update with a caller-supplied drift (integrator-level boundary):
+ * out = (x + h*drift) + c2*(noise*c1), c1 = (float)h^0.5, c2 = (float)(2 ns^2)^0.5.
+ * Replaces BaseSDERungeKuttaIntegrator.step for the EM tableau (core/base_integrator.py:673-731).
+ * `noise` may be NULL when noise_scale < 0 (pure ODE step). */
+int ebm_euler_maruyama_step_f32(const float* x, const float* drift, const float* noise, float* out,
+                                int64_t numel, double step_size, double noise_scale, void* stream);
+
+/* K-step Langevin burst; replaces the loop of LangevinDynamics.sample
+ * (samplers/langevin_dynamics.py:157-185) including gradient, EM update, noise draw, optional clamp
+ * and trajectory thinning, with the chain state resident in registers between steps.
+ *   step_size_host / noise_scale_host: `schedule_len` doubles each; schedule_len is 1 (constant) or n_steps.
+ *   clamp_lo_hi_host: NULL or 2 floats.
+ *   rng_mode INJECTED: `noise` = [n_steps, n, dim]; otherwise (seed, offset) address the Philox stream;
+ *     TORCH consumes n_steps * ebm_torch_rng_offset_increment(n*dim), NATIVE consumes 4 * n_steps.
+ *   traj: NULL or [n, n_steps/thin, dim]; x_out may alias x_in. */
+int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n,
+                           int32_t n_steps, const double* step_size_host, const double* noise_scale_host,
+                           int32_t schedule_len, const float* clamp_lo_hi_host, int32_t rng_mode,
+                           uint64_t seed, uint64_t offset, const float* noise, float* traj, int32_t thin,
+                           void* stream);
+
+/* Same burst with HOST buffers: copies x_in_host -> device scratch, runs the burst, copies the result
+ * back into x_out_host and synchronises `stream`.  `scratch_dev` must hold n*dim floats.
+ * Energy parameter buffers in `e` stay device pointers.  Used for the end-to-end measurement. */
+int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, float* x_out_host,
+                                float* scratch_dev, int64_t n, int32_t n_steps, double step_size,
+                                double noise_scale, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                void* stream);
+
+/* L leapfrog steps; replaces LeapfrogIntegrator.integrate (integrators/leapfrog.py:116-187) for a
+ * recognised energy (drift = -grad E).  safe != 0 applies the +-1e6 force clamp and NaN->0 / inf->FLT_MAX
+ * sanitising of core/base_integrator.py:875-889.  mass_kind/mass_scalar/mass_vec follow leapfrog.py:167-177. */
+int ebm_leapfrog_f32(const EbmEnergyDesc* e, const float* x_in, const float* p_in, float* x_out,
+                     float* p_out, int64_t n, int32_t n_steps, double step_size, int32_t mass_kind,
+                     double mass_scalar, const float* mass_vec, int32_t safe, void* stream);
+
+/* n_proposals HMC proposals; replaces the loop of HamiltonianMonteCarlo.sample (samplers/hmc.py:244-312):
+ * momentum draw, H0, L leapfrog steps (safe mode), H1, Metropolis accept/reject.
+ *   step_size_host: schedule_len (1 or n_proposals) doubles.
+ *   INJECTED: noise_p = [n_proposals, n, dim] standard normals, noise_u = [n_proposals, n] uniforms.
+ *   TORCH consumes per proposal increment(n*dim) + increment(n); NATIVE consumes 8 per proposal.
+ *   traj: NULL or [n, n_proposals/thin, dim].
+ *   accept_count: NULL or int32[n_proposals], += number of accepted chains per proposal (zero it first).
+ *   energy_out: NULL or [n], energy of the final state (clamped to +-1e10 like hmc.py:247). */
+int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n,
+                      int32_t n_proposals, int32_t n_leapfrog, const double* step_size_host,
+                      int32_t schedule_len, int32_t mass_kind, double mass_scalar, const float* mass_vec,
+                      int32_t rng_mode, uint64_t seed, uint64_t offset, const float* noise_p,
+                      const float* noise_u, float* traj, int32_t thin, int32_t* accept_count,
+                      float* energy_out, void* stream);
+
+/* Persistent-CD replay buffer (core/base_loss.py:266-337, :390-426), device side.
+ * gather : out[i, :] = buffer[idx[i], :] (+ 0.01 * noise[j, :] for i = noise_rows[j], j < n_noise).
+ * scatter: FIFO write of `samples` at row `ptr` with wraparound; when batch >= buffer_rows the last
+ *          buffer_rows samples overwrite the whole buffer.  Returns the new ptr through *new_ptr_host. */
+int ebm_pcd_gather_f32(const float* buffer, int64_t buffer_rows, int64_t row_elems, const int64_t* idx,
+                       int64_t batch, float* out, const int64_t* noise_rows, const float* noise,
+                       int64_t n_noise, void* stream);
+int ebm_pcd_scatter_f32(float* buffer, int64_t buffer_rows, int64_t row_elems, int64_t ptr,
+                        const float* samples, int64_t batch, int64_t* new_ptr_host, void* stream);
+
+/* Fill out[numel] with the TORCH- or NATIVE-layout normal (kind 0) / uniform (kind 1) stream at
+ * (seed, offset): test hook that exposes exactly what the fused kernels draw. */
+int ebm_rng_fill_f32(float* out, int64_t numel, int32_t rng_mode, int32_t kind, uint64_t seed,
+                     uint64_t offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBM_B200_H */

@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/ebm_b200.h declares."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ebm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ebm_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from torchebm_b200 import _lib, build
+
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from torchebm_b200 import _lib
+
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    assert sorted(_lib.PROTOTYPES) == declared, "binding table and header disagree"
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_abi_version_and_argument_errors_need_no_gpu(lib):
+    from torchebm_b200 import _lib
+
+    assert lib.ebm_abi_version() == _lib.EBM_ABI_VERSION
+    # null descriptor -> EBM_ERR_INVALID before anything touches the device
+    rc = lib.ebm_energy_f32(None, None, 1, None, None)
+    assert rc == _lib.ERR_INVALID
+    assert b"descriptor" in lib.ebm_last_error()
+    d = _lib.EbmEnergyDesc()
+    d.kind, d.dim = _lib.ENERGY_DOUBLE_WELL, 4
+    rc = lib.ebm_langevin_burst_f32(ctypes.byref(d), None, None, 8, 3, None, None, 1, None, 1, 0, 0, None, None, 1, None)
+    assert rc == _lib.ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(rc, "ebm_langevin_burst_f32")
+
+
+def test_missing_library_raises_instead_of_falling_back(monkeypatch, tmp_path):
+    from torchebm_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.EbmLibraryError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "torchebm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

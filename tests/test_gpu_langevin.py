@@ -1,0 +1,309 @@
+"""Parity of the fused Langevin bursts (through the C ABI) with the oracle and the reference goldens.
+
+Bars (fp32):
+* elementwise energies without transcendentals (DoubleWell, Harmonic), injected noise: BIT-EXACT vs the
+  reference golden (the kernel reproduces the reference's rounding order);
+* Rastrigin: device sinf vs host sin differ by <= 1 ulp per call, so atol 2e-6 / rtol 1e-5 over 20 steps;
+* Gaussian / MoG / MLP (reordered reductions): atol 2e-5 / rtol 1e-4 vs the golden for K <= 20,
+  and the K=100 DoubleWell case within the reference's own sensitivity;
+* same seed, rng="torch": identical to the oracle run on CUDA with the same generator (bit-exact for the
+  elementwise energies).
+"""
+
+import pytest
+import torch
+
+from oracle import energies as E
+from oracle import langevin as olang
+
+from . import _cases as C
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _model_for(name, g):
+    import torchebm_b200 as te
+
+    if "doublewell" in name or name in ("langevin_single_chain", "langevin_scheduled"):
+        return te.DoubleWellModel(g.get("barrier_height", 2.0), g.get("b", 1.0))
+    if "harmonic" in name:
+        return te.HarmonicModel(g["kspring"])
+    if "rastrigin" in name:
+        return te.RastriginModel(g["a"])
+    if "gaussian" in name:
+        return te.GaussianModel(g["mean"], g["cov"]).to(DEV)
+    if "mog" in name:
+        return te.MixtureOfGaussiansModel(g["means"], g["sigmas"], g["weights"]).to(DEV)
+    act = "tanh" if "tanh" in name else "silu"
+    d, h = g["w0"].shape[1], g["w0"].shape[0]
+    m = te.MLPEnergy(dim=d, hidden=h, activation=act)
+    lin = [l for l in m.net if isinstance(l, torch.nn.Linear)]
+    with torch.no_grad():
+        for i, l in enumerate(lin):
+            l.weight.copy_(g[f"w{i}"])
+            l.bias.copy_(g[f"b{i}"])
+    return m.to(DEV)
+
+
+EXACT = {"langevin_doublewell", "langevin_doublewell_odd", "langevin_harmonic", "langevin_single_chain",
+         "langevin_scheduled"}
+
+
+@pytest.mark.parametrize("name", C.LANGEVIN_CASES)
+def test_energy_and_gradient_match_reference(name):
+    import torchebm_b200 as te
+    from torchebm_b200 import ops
+
+    g = C.load(name)
+    model = _model_for(name, g)
+    x0 = g["x0"].to(DEV)
+    desc = te.energy_descriptor(model, x0.shape[1], x0.device)
+    assert desc is not None
+    grad = ops.gradient(desc, x0).cpu()
+    en = ops.energy(desc, x0).cpu()
+    if name in EXACT or name == "langevin_doublewell_k100":
+        assert torch.equal(grad, g["grad0"])
+    else:
+        torch.testing.assert_close(grad, g["grad0"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(en, g["energy0"], rtol=1e-5, atol=1e-4)
+    # BaseModel.gradient routes to the same kernel
+    assert torch.equal(model.gradient(x0).cpu(), grad)
+
+
+@pytest.mark.parametrize("name", C.LANGEVIN_CASES)
+def test_injected_noise_burst_matches_reference_golden(name):
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    g = C.load(name)
+    model = _model_for(name, g)
+    x0 = g["x0"].to(DEV)
+    k = int(g["k"])
+    h, ns = C.langevin_schedule(name, g)
+    hs, nss = (h, ns) if isinstance(h, list) else ([h], [ns])
+    kw = C.langevin_kwargs(name, g)
+    desc = te.energy_descriptor(model, x0.shape[1], x0.device)
+    noise = C.langevin_noise(g).to(DEV)
+    thin = kw.get("thin", 1)
+    traj = None
+    if kw.get("return_trajectory"):
+        traj = torch.empty(x0.shape[0], k // thin, x0.shape[1], device=DEV)
+    out = ops.langevin_burst(desc, x0, k, hs, nss, clamp=kw.get("clamp"), rng_mode=_lib.RNG_INJECTED, noise=noise,
+                             traj=traj, thin=thin)
+    got = (traj if traj is not None else out).cpu()
+    if name in EXACT:
+        assert torch.equal(got, g["out"])
+    elif name == "langevin_doublewell_k100":
+        d = (got - g["out"]).abs()
+        assert d.max() <= 2e-4 and d.mean() <= 1e-6  # chaotic amplification bound, SURVEY.md A.2
+    elif name == "langevin_rastrigin":
+        torch.testing.assert_close(got, g["out"], rtol=1e-5, atol=2e-6)
+    else:
+        torch.testing.assert_close(got, g["out"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["langevin_doublewell_odd", "langevin_single_chain"])
+def test_sampler_diagnostics_match_reference_golden(name):
+    """Through the sampler API: trajectory, thin, clamp and the diagnostics dict."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    g = C.load(name)
+    model = _model_for(name, g)
+    kw = C.langevin_kwargs(name, g)
+    clamp = kw.pop("clamp", None)
+    sampler = te.LangevinDynamics(model, step_size=float(g["h"]), noise_scale=float(g["ns"]), clamp=clamp, device=DEV)
+    # the sampler draws its own noise; to compare with the golden, inject the golden noise by monkeypatching
+    noise = C.langevin_noise(g).to(DEV)
+    calls = {"i": 0}
+    real = ops.langevin_burst
+
+    def injected(desc, x, n_steps, hs, nss, **k2):
+        i = calls["i"]
+        calls["i"] += n_steps
+        k2.update(rng_mode=_lib.RNG_INJECTED, noise=noise[i:i + n_steps].contiguous())
+        return real(desc, x, n_steps, hs, nss, **k2)
+
+    ops.langevin_burst = injected
+    try:
+        res = sampler.sample(x=g["x0"].to(DEV), n_steps=int(g["k"]), **kw)
+    finally:
+        ops.langevin_burst = real
+    out, diag = res
+    assert torch.equal(out.cpu(), g["out"])
+    torch.testing.assert_close(diag["mean"].cpu(), g["diag_mean"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(diag["var"].cpu(), g["diag_var"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(diag["energy"].cpu(), g["diag_energy"], rtol=1e-5, atol=1e-5)
+
+
+def _oracle_for(name, g):
+    en = C.energy_for(name, g)
+    return en.to(DEV) if hasattr(en, "to") else en
+
+
+@pytest.mark.parametrize("name,n,d,k", [
+    ("langevin_doublewell", 4096, 128, 20),
+    ("langevin_doublewell", 5000, 77, 7),       # numel not a multiple of anything
+    ("langevin_doublewell", 65536, 128, 3),     # numel > T: the unrolled quad layout
+    ("langevin_harmonic", 3000, 10, 10),
+    ("langevin_rastrigin", 2048, 64, 10),
+    ("langevin_gaussian_d16", 2000, 16, 10),
+    ("langevin_mog", 2000, 6, 10),
+    ("langevin_mlp_silu", 1000, 16, 5),
+    ("langevin_mlp_d128", 4096, 128, 5),
+])
+def test_same_seed_matches_reference_stream_on_cuda(name, n, d, k):
+    """rng='torch': the sampler consumes torch's CUDA Philox stream exactly like the reference's per-step
+    randn_like, so the oracle (same torch ops as the reference) run on CUDA with an equal-seeded generator
+    must give the same chains, and both generators must end at the same offset."""
+    import torchebm_b200 as te
+
+    g = C.load(name)
+    model = _model_for(name, g)
+    en = _oracle_for(name, g)
+    x0 = torch.randn(n, d, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+    sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV)
+    g1 = torch.Generator(DEV).manual_seed(11)
+    g2 = torch.Generator(DEV).manual_seed(11)
+    got = sampler.sample(x=x0, n_steps=k, generator=g1)
+    want = olang.sample(en, x0, k, 0.01, 1.0, generator=g2)
+    assert g1.get_offset() == g2.get_offset()
+    if "doublewell" in name or "harmonic" in name:
+        assert torch.equal(got, want)
+    elif "rastrigin" in name:
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-6)
+    else:
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
+    # global-RNG path: generator=None consumes the device default generator the same way
+    torch.manual_seed(5)
+    a = sampler.sample(x=x0, n_steps=2)
+    torch.manual_seed(5)
+    b = olang.sample(en, x0, 2, 0.01, 1.0)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5)
+
+
+def test_x_none_draws_initial_state_from_generator():
+    import torchebm_b200 as te
+
+    sampler = te.LangevinDynamics(te.DoubleWellModel(), step_size=0.01, device=DEV)
+    g1 = torch.Generator(DEV).manual_seed(8)
+    g2 = torch.Generator(DEV).manual_seed(8)
+    got = sampler.sample(dim=5, n_samples=300, n_steps=4, generator=g1)
+    x0 = torch.randn(300, 5, device=DEV, generator=g2)
+    want = olang.sample(E.DoubleWell(), x0, 4, 0.01, 1.0, generator=g2)
+    assert torch.equal(got, want)
+
+
+def test_input_not_mutated_and_in_place_variant():
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    x0 = torch.randn(1000, 32, device=DEV)
+    keep = x0.clone()
+    sampler = te.LangevinDynamics(te.DoubleWellModel(), step_size=0.01, device=DEV)
+    out = sampler.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(0))
+    assert torch.equal(x0, keep) and out.data_ptr() != x0.data_ptr()
+    desc = te.energy_descriptor(te.DoubleWellModel(), 32, x0.device)
+    x1 = x0.clone()
+    ops.langevin_burst(desc, x1, 5, [0.01], [1.0], rng_mode=_lib.RNG_TORCH, seed=0, offset=0, out=x1)
+    assert torch.equal(x1, out)
+
+
+def test_native_rng_is_deterministic_and_well_distributed():
+    import torchebm_b200 as te
+
+    sampler = te.LangevinDynamics(te.HarmonicModel(k=1.0), step_size=0.05, noise_scale=1.0, device=DEV, rng="native")
+    x0 = torch.zeros(20000, 8, device=DEV)
+    a = sampler.sample(x=x0, n_steps=400, generator=torch.Generator(DEV).manual_seed(1))
+    b = sampler.sample(x=x0, n_steps=400, generator=torch.Generator(DEV).manual_seed(1))
+    c = sampler.sample(x=x0, n_steps=400, generator=torch.Generator(DEV).manual_seed(2))
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # OU stationary law for dx = -k x dt + sqrt(2) dW discretised with h: var = 1 / (k (1 - h k / 2))
+    var = a.var().item()
+    assert abs(var - 1.0 / (1.0 - 0.025)) < 0.05
+    assert abs(a.mean().item()) < 0.02
+
+
+def test_scheduled_burst_longer_than_one_table_chunk():
+    """Per-step schedules are shipped in 64-step tables; cross the chunk boundary and check against the oracle."""
+    import torchebm_b200 as te
+
+    k = 150
+    hs = te.ExponentialDecayScheduler(start_value=0.02, decay_rate=0.99, min_value=0.001)
+    nss = te.LinearScheduler(start_value=1.0, end_value=0.2, n_steps=k)
+    sampler = te.LangevinDynamics(te.DoubleWellModel(), step_size=hs, noise_scale=nss, device=DEV)
+    x0 = torch.randn(512, 8, device=DEV)
+    got, diag = sampler.sample(x=x0, n_steps=k, thin=7, return_trajectory=True, return_diagnostics=True,
+                               generator=torch.Generator(DEV).manual_seed(4))
+    assert hs.step_count == k and nss.step_count == k
+    hv = [max(0.001, 0.02 * 0.99**i) for i in range(k)]
+    nv = [1.0 + (0.2 - 1.0) / k * i for i in range(k)]
+    want, wdiag = olang.sample(E.DoubleWell(), x0, k, hv, nv, thin=7, return_trajectory=True, return_diagnostics=True,
+                               generator=torch.Generator(DEV).manual_seed(4))
+    assert got.shape == (512, k // 7, 8)
+    d = (got - want).abs()
+    assert d.max() <= 5e-4 and d.mean() <= 1e-6
+    torch.testing.assert_close(diag["energy"], wdiag["energy"], rtol=1e-4, atol=1e-4)
+    # trajectory in one launch == trajectory with diagnostics (one launch per kept sample)
+    got2 = sampler.sample(x=x0, n_steps=k, thin=7, return_trajectory=True, generator=torch.Generator(DEV).manual_seed(4))
+    assert torch.equal(got, got2)
+
+
+def test_errors_match_reference_contract():
+    import torchebm_b200 as te
+
+    m = te.DoubleWellModel()
+    with pytest.raises(ValueError, match="step_size must be positive"):
+        te.LangevinDynamics(m, step_size=-1.0)
+    with pytest.raises(ValueError, match="clamp min must be < max"):
+        te.LangevinDynamics(m, clamp=(1.0, 0.0))
+    s = te.LangevinDynamics(m, device=DEV)
+    with pytest.raises(ValueError, match="thin must be >= 1"):
+        s.sample(dim=2, n_steps=3, thin=0)
+    with pytest.raises(ValueError, match="dim must be provided"):
+        s.sample(n_steps=3)
+    with pytest.raises(RuntimeError, match="[Gg]enerator"):
+        s.sample(dim=2, n_steps=3, generator=torch.Generator().manual_seed(0))
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        te.LangevinDynamics(m, device="cpu").sample(dim=2, n_steps=1)
+
+
+def test_opaque_energy_uses_integrator_boundary():
+    """A user energy the library does not recognise keeps its own autograd gradient; the update runs in
+    ebm_euler_maruyama_step_f32 and matches the oracle bit for bit."""
+    import torchebm_b200 as te
+
+    class Quartic(te.BaseModel):
+        def forward(self, x):
+            return (x**4).sum(-1) * 0.1
+
+    class QuarticO(E.Energy):
+        def energy(self, x):
+            return (x**4).sum(-1) * 0.1
+
+    sampler = te.LangevinDynamics(Quartic(), step_size=0.01, device=DEV)
+    x0 = torch.randn(256, 4, device=DEV)
+    got = sampler.sample(x=x0, n_steps=6, generator=torch.Generator(DEV).manual_seed(2))
+    want = olang.sample(QuarticO(), x0, 6, 0.01, 1.0, generator=torch.Generator(DEV).manual_seed(2))
+    assert torch.equal(got, want)
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (65536 x 128, K=500): determinism, finiteness, stationary moments."""
+    import torchebm_b200 as te
+
+    sampler = te.LangevinDynamics(te.DoubleWellModel(2.0, 1.0), step_size=0.01, noise_scale=1.0, device=DEV)
+    x0 = torch.randn(65536, 128, device=DEV, generator=torch.Generator(DEV).manual_seed(0))
+    a = sampler.sample(x=x0, n_steps=500, generator=torch.Generator(DEV).manual_seed(1))
+    b = sampler.sample(x=x0, n_steps=500, generator=torch.Generator(DEV).manual_seed(1))
+    assert torch.equal(a, b)
+    assert torch.isfinite(a).all()
+    # population statistics of the reference chain after 500 steps: E|x| = 0.8575, var = 0.8397
+    assert abs(a.abs().mean().item() - 0.8575) < 5e-3
+    assert abs(a.var().item() - 0.8397) < 5e-3
+    # burst composition: 500 steps == 200 + 300 steps with a continued generator
+    g = torch.Generator(DEV).manual_seed(1)
+    c = sampler.sample(x=sampler.sample(x=x0, n_steps=200, generator=g), n_steps=300, generator=g)
+    assert torch.equal(a, c)

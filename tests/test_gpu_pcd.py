@@ -1,0 +1,126 @@
+"""Persistent-CD replay buffer on the device and the ContrastiveDivergence loss driving a fused sampler."""
+
+import pytest
+import torch
+
+from oracle import energies as E
+from oracle import langevin as olang
+from oracle import pcd as opcd
+
+from . import _cases as C
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def test_gather_scatter_kernels_match_oracle_fifo():
+    from torchebm_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    buf = torch.randn(50, 3, 4, generator=g)
+    dbuf = buf.to(DEV).clone()
+    ob = opcd.ReplayBuffer(50)
+    ob.buffer = buf.clone()
+    ptr = 0
+    for b in (16, 16, 16, 16, 7, 50, 64):
+        samples = torch.randn(b, 3, 4, generator=g)
+        ob.update(samples)
+        ptr = ops.pcd_scatter(dbuf, ptr, samples.to(DEV))
+        assert ptr == ob.ptr
+        assert torch.equal(dbuf.cpu(), ob.buffer)
+    idx = torch.randint(0, 50, (20,), generator=g)
+    rows = torch.randperm(20, generator=g)[:5]
+    noise = torch.randn(5, 3, 4, generator=g)
+    want = ob.buffer[idx]
+    want[rows] = want[rows] + noise * 0.01
+    got = ops.pcd_gather(dbuf, idx.to(DEV), rows.to(DEV), noise.to(DEV))
+    assert torch.equal(got.cpu(), want)
+
+
+def test_cd_persistent_sequence_matches_oracle_on_cuda():
+    """Same seed: buffer init, stratified indices, exploration noise, K-step chain, FIFO write-back and the loss
+    all agree with the oracle (which is pinned to the reference's own CD run in tests/test_oracle_golden.py)."""
+    import torchebm_b200 as te
+
+    g = C.load("pcd_mlp_tanh")
+    model = te.MLPEnergy(dim=6, hidden=8, activation="tanh")
+    lin = [l for l in model.net if isinstance(l, torch.nn.Linear)]
+    with torch.no_grad():
+        for i, l in enumerate(lin):
+            l.weight.copy_(g[f"w{i}"])
+            l.bias.copy_(g[f"b{i}"])
+    model = model.to(DEV)
+    sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV)
+    cd = te.ContrastiveDivergence(model, sampler, k_steps=3, persistent=True, buffer_size=40, init_steps=0,
+                                  new_sample_ratio=0.25, energy_reg_weight=0.001, device=DEV)
+    en = C.mlp_from(g, "tanh").to(DEV)
+    g1 = torch.Generator(DEV).manual_seed(77)
+    g2 = torch.Generator(DEV).manual_seed(77)
+    ob = opcd.ReplayBuffer(40, new_sample_ratio=0.25)
+    for it in range(4):
+        x = g["data"][it].to(DEV)
+        loss, neg = cd(x, generator=g1)
+        if ob.buffer is None:
+            ob.initialize((6,), DEV, generator=g2)
+        start = ob.get_start_points(16, generator=g2)
+        wneg = olang.sample(en, start, 3, 0.01, 1.0, generator=g2)
+        ob.update(wneg)
+        torch.testing.assert_close(neg, wneg, rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(cd.replay_buffer, ob.buffer, rtol=1e-4, atol=2e-5)
+        assert cd._buffer_ptr_int == ob.ptr == int(cd.buffer_ptr.item())
+        assert g1.get_offset() == g2.get_offset()
+        xe, ne = en.energy(x), en.energy(wneg)
+        wloss = xe.mean() - ne.mean() + 0.001 * ((xe**2).mean() + (ne**2).mean())
+        torch.testing.assert_close(loss, wloss, rtol=1e-4, atol=1e-5)
+    assert loss.requires_grad
+    loss.backward()
+    assert all(p.grad is not None for p in model.parameters())
+
+
+def test_cd_fifo_pointer_and_state_dict_roundtrip():
+    import torchebm_b200 as te
+
+    model = te.DoubleWellModel(2.0, 1.0)
+    sampler = te.LangevinDynamics(model, step_size=0.01, device=DEV)
+    cd = te.ContrastiveDivergence(model, sampler, k_steps=2, persistent=True, buffer_size=50, init_steps=0,
+                                  new_sample_ratio=0.0, device=DEV)
+    ptrs = []
+    for it in range(5):
+        cd(torch.randn(16, 3, device=DEV))
+        ptrs.append(cd._buffer_ptr_int)
+    assert ptrs == [16, 32, 48, 14, 30]  # tests/losses/test_contrastive_divergence.py:419-453 arithmetic
+    sd = cd.state_dict()
+    assert "replay_buffer" in sd and "buffer_ptr" in sd
+    cd2 = te.ContrastiveDivergence(model, sampler, k_steps=2, persistent=True, buffer_size=50, init_steps=0, device=DEV)
+    cd2.initialize_buffer((3,))
+    cd2.load_state_dict(sd)
+    assert cd2._buffer_ptr_int == 30 and torch.equal(cd2.replay_buffer, cd.replay_buffer)
+
+
+def test_cd_buffer_warmup_and_full_overwrite():
+    """init_steps > 0 runs the sampler over 1024-row chunks (base_loss.py:236-246); batch == buffer overwrites all."""
+    import torchebm_b200 as te
+
+    model = te.DoubleWellModel(2.0, 1.0)
+    sampler = te.LangevinDynamics(model, step_size=0.01, device=DEV)
+    cd = te.ContrastiveDivergence(model, sampler, k_steps=5, persistent=True, buffer_size=2048, init_steps=10,
+                                  new_sample_ratio=0.05, device=DEV)
+    loss, neg = cd(torch.randn(2048, 4, device=DEV), generator=torch.Generator(DEV).manual_seed(0))
+    assert neg.shape == (2048, 4) and torch.isfinite(loss)
+    assert cd._buffer_ptr_int == 0 and torch.equal(cd.replay_buffer, neg)
+
+
+def test_c3_shape_cd_step_runs_fused():
+    """BASELINE config 3 shape at reduced width (D=128: this build's MLP kernel limit): persistent CD, N=65536, k=20."""
+    import torchebm_b200 as te
+
+    torch.manual_seed(0)
+    model = te.MLPEnergy(dim=128, hidden=128, activation="silu").to(DEV)
+    sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV)
+    cd = te.ContrastiveDivergence(model, sampler, k_steps=20, persistent=True, buffer_size=65536, init_steps=0,
+                                  new_sample_ratio=0.0, device=DEV)
+    x = torch.randn(65536, 128, device=DEV)
+    loss, neg = cd(x, generator=torch.Generator(DEV).manual_seed(0))
+    assert torch.isfinite(neg).all() and torch.isfinite(loss)
+    loss.backward()

@@ -1,0 +1,407 @@
+// C-ABI: library bookkeeping, RNG test hook, energy/gradient, Euler-Maruyama step, Langevin bursts
+// for the analytic energies, persistent-CD buffer gather/scatter.  See include/ebm_b200.h.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "api_common.cuh"
+
+namespace ebm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+const DeviceInfo& device_info(int device) {
+  static DeviceInfo info[64];
+  static bool have[64] = {false};
+  static std::mutex mu;
+  if (device < 0 || device >= 64) device = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!have[device]) {
+    DeviceInfo di{148, 2048, 227 * 1024};
+    cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&di.max_threads_per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, device);
+    cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    info[device] = di;
+    have[device] = true;
+  }
+  return info[device];
+}
+
+// ---- RNG test hook ---------------------------------------------------------------------------
+__global__ void rng_fill_kernel(float* out, long long numel, RngStream s, int kind) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < numel; li += stride)
+    out[li] = kind == 0 ? normal_for_element(s, (uint64_t)li) : uniform_for_element(s, (uint64_t)li);
+}
+
+// ---- Euler-Maruyama step with an opaque drift ------------------------------------------------
+__global__ void em_step_kernel(const float* __restrict__ x, const float* __restrict__ drift,
+                               const float* __restrict__ noise, float* __restrict__ out, long long numel, float h,
+                               float c1, float c2, int has_noise) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    float v = __fadd_rn(x[i], __fmul_rn(h, drift[i]));
+    if (has_noise) v = __fadd_rn(v, __fmul_rn(c2, __fmul_rn(noise[i], c1)));
+    out[i] = v;
+  }
+}
+
+// ---- persistent-CD buffer ----------------------------------------------------------------------
+__global__ void pcd_gather_kernel(const float* __restrict__ buffer, long long row_elems, const long long* __restrict__ idx,
+                                  long long batch, float* __restrict__ out) {
+  const long long total = batch * row_elems;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / row_elems, c = i - r * row_elems;
+    out[i] = buffer[idx[r] * row_elems + c];
+  }
+}
+__global__ void pcd_noise_kernel(float* __restrict__ out, long long row_elems, const long long* __restrict__ rows,
+                                 const float* __restrict__ noise, long long n_noise) {
+  const long long total = n_noise * row_elems;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long j = i / row_elems, c = i - j * row_elems;
+    float* p = out + rows[j] * row_elems + c;
+    *p = __fadd_rn(*p, __fmul_rn(noise[i], 0.01f));  // base_loss.py:322-331
+  }
+}
+__global__ void pcd_scatter_kernel(float* __restrict__ buffer, long long buffer_rows, long long row_elems, long long ptr,
+                                   const float* __restrict__ samples, long long batch) {
+  const long long total = batch * row_elems;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / row_elems, c = i - r * row_elems;
+    long long dst = ptr + r;
+    if (dst >= buffer_rows) dst -= buffer_rows;
+    buffer[dst * row_elems + c] = samples[i];
+  }
+}
+
+static inline int flat_grid(const DeviceInfo& di, long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)di.sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- energy / gradient dispatch ---------------------------------------------------------------
+template <class RowE>
+static int launch_energy_grad(const RowE& en, const EbmEnergyDesc* e, const float* x, int64_t n, float* energy,
+                              float* grad, cudaStream_t st) {
+  const DeviceInfo& di = device_info(current_device());
+#define CALL(G, E)                                                                                  \
+  {                                                                                                 \
+    int ss;                                                                                         \
+    const size_t smem = row_smem_bytes(e, G, ss);                                                   \
+    if (smem > (size_t)di.max_smem_optin) { set_error("energy parameters need %zu B of shared memory", smem); return EBM_ERR_UNSUPPORTED; } \
+    auto kern = row_energy_grad_kernel<RowE, G, E>;                                                 \
+    if (smem > 48 * 1024) EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<row_grid(di, n, G, 8), kRowThreads, smem, st>>>(en, x, n, e->dim, energy, grad, ss);     \
+  }
+  EBM_ROW_DISPATCH(e->dim, CALL);
+#undef CALL
+  return launch_status("row_energy_grad_kernel");
+}
+
+// ---- Langevin dispatch ------------------------------------------------------------------------
+
+template <class ElemE>
+static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
+  const DeviceInfo& di = device_info(current_device());
+  const long long numel = (long long)c.n * c.e->dim;
+  LangevinElemParams P;
+  memset(&P, 0, sizeof(P));
+  P.numel = numel;
+  P.d = c.e->dim;
+  P.thin = c.thin;
+  P.n_kept = c.n_steps / c.thin;
+  P.has_clamp = c.clamp != nullptr;
+  if (c.clamp) { P.clamp_lo = c.clamp[0]; P.clamp_hi = c.clamp[1]; }
+  P.traj = c.traj;
+  if (c.rng_mode == EBM_RNG_TORCH) {
+    P.T = torch_threads(di, numel);
+    const unsigned long long J = (((unsigned long long)numel + P.T - 1) / P.T + 3) / 4;
+    P.n_quads = P.T * J;
+    P.k0 = (uint32_t)c.seed; P.k1 = (uint32_t)(c.seed >> 32);
+    P.ctr_step = torch_offset_increment(di, numel) / 4;
+  } else {
+    P.T = 1;
+    P.n_quads = ((unsigned long long)numel + 3) / 4;
+    P.k0 = (uint32_t)c.seed ^ kNativeTag0; P.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
+    P.ctr_step = 1;
+  }
+  const unsigned long long blocks = (P.n_quads + 255) / 256;
+  if (blocks > 0x7fffffffull) { set_error("too many elements"); return EBM_ERR_UNSUPPORTED; }
+
+  const bool uniform = c.schedule_len == 1;
+  int done = 0;
+  const float* src = c.x_in;
+  while (done < c.n_steps) {
+    const int chunk = uniform ? c.n_steps : ((c.n_steps - done < kSchedChunk) ? (c.n_steps - done) : kSchedChunk);
+    StepTable tab;
+    memset(&tab, 0, sizeof(tab));
+    if (uniform) { fill_step(tab, 0, c.hs[0], c.nss[0]); tab.mask = 0; }
+    else { for (int i = 0; i < chunk; ++i) fill_step(tab, i, c.hs[done + i], c.nss[done + i]); tab.mask = ~0; }
+    P.x_in = src;
+    P.x_out = c.x_out;
+    P.n_steps = chunk;
+    P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
+    P.ctr_base = c.offset / 4 + (unsigned long long)done * P.ctr_step;
+    P.thin_start = c.thin - (done % c.thin);
+    P.kept_base = done / c.thin;
+#define LAUNCH(RNG)                                                                                         \
+  if (c.traj) langevin_elem_kernel<ElemE, RNG, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);        \
+  else        langevin_elem_kernel<ElemE, RNG, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);
+    if (c.rng_mode == EBM_RNG_INJECTED) { LAUNCH(0) }
+    else if (c.rng_mode == EBM_RNG_TORCH) { LAUNCH(1) }
+    else { LAUNCH(2) }
+#undef LAUNCH
+    int rc = launch_status("langevin_elem_kernel");
+    if (rc) return rc;
+    done += chunk;
+    src = c.x_out;
+  }
+  return 0;
+}
+
+template <class RowE>
+static int launch_langevin_row(const RowE& en, const LangevinCall& c) {
+  const DeviceInfo& di = device_info(current_device());
+  const long long numel = (long long)c.n * c.e->dim;
+  LangevinRowParams P;
+  memset(&P, 0, sizeof(P));
+  P.n = c.n;
+  P.d = c.e->dim;
+  P.thin = c.thin;
+  P.n_kept = c.n_steps / c.thin;
+  P.has_clamp = c.clamp != nullptr;
+  if (c.clamp) { P.clamp_lo = c.clamp[0]; P.clamp_hi = c.clamp[1]; }
+  P.traj = c.traj;
+  P.rng.mode = c.rng_mode;
+  if (c.rng_mode == EBM_RNG_TORCH) {
+    P.rng.T = torch_threads(di, numel);
+    P.rng.k0 = (uint32_t)c.seed; P.rng.k1 = (uint32_t)(c.seed >> 32);
+    P.rng.ctr_step = torch_offset_increment(di, numel) / 4;
+  } else {
+    P.rng.T = 1;
+    P.rng.k0 = (uint32_t)c.seed ^ kNativeTag0; P.rng.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
+    P.rng.ctr_step = 1;
+  }
+  const bool uniform = c.schedule_len == 1;
+  int done = 0;
+  const float* src = c.x_in;
+  while (done < c.n_steps) {
+    const int chunk = uniform ? c.n_steps : ((c.n_steps - done < kSchedChunk) ? (c.n_steps - done) : kSchedChunk);
+    StepTable tab;
+    memset(&tab, 0, sizeof(tab));
+    if (uniform) { fill_step(tab, 0, c.hs[0], c.nss[0]); tab.mask = 0; }
+    else { for (int i = 0; i < chunk; ++i) fill_step(tab, i, c.hs[done + i], c.nss[done + i]); tab.mask = ~0; }
+    P.x_in = src;
+    P.x_out = c.x_out;
+    P.n_steps = chunk;
+    P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
+    P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;
+    P.thin_start = c.thin - (done % c.thin);
+    P.kept_base = done / c.thin;
+#define CALL(G, E)                                                                                  \
+  {                                                                                                 \
+    int ss;                                                                                         \
+    const size_t smem = row_smem_bytes(c.e, G, ss);                                                 \
+    if (smem > (size_t)di.max_smem_optin) { set_error("energy parameters need %zu B of shared memory", smem); return EBM_ERR_UNSUPPORTED; } \
+    P.scratch_stride = ss;                                                                          \
+    auto kern = langevin_row_kernel<RowE, G, E>;                                                    \
+    if (smem > 48 * 1024) EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<row_grid(di, c.n, G, 4), kRowThreads, smem, c.st>>>(en, P, tab);                         \
+  }
+    EBM_ROW_DISPATCH(c.e->dim, CALL);
+#undef CALL
+    int rc = launch_status("langevin_row_kernel");
+    if (rc) return rc;
+    done += chunk;
+    src = c.x_out;
+  }
+  return 0;
+}
+
+int langevin_mlp_dispatch(const LangevinCall& c);  // ebm_mlp.cu
+
+static int langevin_dispatch(const LangevinCall& c) {
+  switch (c.e->kind) {
+    case EBM_ENERGY_DOUBLE_WELL: return launch_langevin_elem(make_dw(c.e), c);
+    case EBM_ENERGY_HARMONIC: return launch_langevin_elem(make_harm(c.e), c);
+    case EBM_ENERGY_RASTRIGIN: return launch_langevin_elem(make_rast(c.e), c);
+    case EBM_ENERGY_GAUSSIAN: return launch_langevin_row(make_gauss(c.e), c);
+    case EBM_ENERGY_MOG: return launch_langevin_row(make_mog(c.e), c);
+    case EBM_ENERGY_MLP: return langevin_mlp_dispatch(c);
+  }
+  return EBM_ERR_INVALID;
+}
+
+int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
+                             cudaStream_t st);  // ebm_mlp.cu
+
+}  // namespace ebm
+
+using namespace ebm;
+
+extern "C" {
+
+int ebm_abi_version(void) { return EBM_ABI_VERSION; }
+const char* ebm_last_error(void) { return g_err; }
+
+int ebm_device_sm_count(int device) { return device_info(device).sm_count; }
+int64_t ebm_torch_rng_threads(int device, int64_t numel) { return (int64_t)torch_threads(device_info(device), numel); }
+int64_t ebm_torch_rng_offset_increment(int device, int64_t numel) {
+  return (int64_t)torch_offset_increment(device_info(device), numel);
+}
+
+int ebm_rng_fill_f32(float* out, int64_t numel, int32_t rng_mode, int32_t kind, uint64_t seed, uint64_t offset,
+                     void* stream) {
+  EBM_CHECK_ARG(out && numel > 0, "out must be non-null and numel positive");
+  EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "rng_mode must be TORCH or NATIVE");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  const DeviceInfo& di = device_info(current_device());
+  RngStream s;
+  s.mode = rng_mode;
+  s.ctr_base = offset / 4;
+  if (rng_mode == EBM_RNG_TORCH) { s.T = torch_threads(di, numel); s.k0 = (uint32_t)seed; s.k1 = (uint32_t)(seed >> 32); }
+  else { s.T = 1; s.k0 = (uint32_t)seed ^ kNativeTag0; s.k1 = (uint32_t)(seed >> 32) ^ kNativeTag1; }
+  rng_fill_kernel<<<flat_grid(di, numel, 256), 256, 0, (cudaStream_t)stream>>>(out, numel, s, kind);
+  return launch_status("rng_fill_kernel");
+}
+
+int ebm_energy_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x && energy && n > 0, "x/energy must be non-null and n positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (e->kind) {
+    case EBM_ENERGY_DOUBLE_WELL: return launch_energy_grad(ElemRow<DoubleWellE>{make_dw(e)}, e, x, n, energy, nullptr, st);
+    case EBM_ENERGY_HARMONIC: return launch_energy_grad(ElemRow<HarmonicE>{make_harm(e)}, e, x, n, energy, nullptr, st);
+    case EBM_ENERGY_RASTRIGIN: return launch_energy_grad(ElemRow<RastriginE>{make_rast(e)}, e, x, n, energy, nullptr, st);
+    case EBM_ENERGY_GAUSSIAN: return launch_energy_grad(make_gauss(e), e, x, n, energy, nullptr, st);
+    case EBM_ENERGY_MOG: return launch_energy_grad(make_mog(e), e, x, n, energy, nullptr, st);
+    case EBM_ENERGY_MLP: return mlp_energy_grad_dispatch(e, x, n, energy, nullptr, st);
+  }
+  return EBM_ERR_INVALID;
+}
+
+int ebm_gradient_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* grad, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x && grad && n > 0, "x/grad must be non-null and n positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (e->kind) {
+    case EBM_ENERGY_DOUBLE_WELL: return launch_energy_grad(ElemRow<DoubleWellE>{make_dw(e)}, e, x, n, nullptr, grad, st);
+    case EBM_ENERGY_HARMONIC: return launch_energy_grad(ElemRow<HarmonicE>{make_harm(e)}, e, x, n, nullptr, grad, st);
+    case EBM_ENERGY_RASTRIGIN: return launch_energy_grad(ElemRow<RastriginE>{make_rast(e)}, e, x, n, nullptr, grad, st);
+    case EBM_ENERGY_GAUSSIAN: return launch_energy_grad(make_gauss(e), e, x, n, nullptr, grad, st);
+    case EBM_ENERGY_MOG: return launch_energy_grad(make_mog(e), e, x, n, nullptr, grad, st);
+    case EBM_ENERGY_MLP: return mlp_energy_grad_dispatch(e, x, n, nullptr, grad, st);
+  }
+  return EBM_ERR_INVALID;
+}
+
+int ebm_euler_maruyama_step_f32(const float* x, const float* drift, const float* noise, float* out, int64_t numel,
+                                double step_size, double noise_scale, void* stream) {
+  EBM_CHECK_ARG(x && drift && out && numel > 0, "x/drift/out must be non-null and numel positive");
+  const bool has_noise = noise_scale >= 0.0;
+  EBM_CHECK_ARG(!has_noise || noise, "noise must be given when noise_scale >= 0");
+  const DeviceInfo& di = device_info(current_device());
+  StepTable t;
+  fill_step(t, 0, step_size, has_noise ? noise_scale : 0.0);
+  em_step_kernel<<<flat_grid(di, numel, 256), 256, 0, (cudaStream_t)stream>>>(x, drift, noise, out, numel, t.h[0],
+                                                                              t.c1[0], t.c2[0], has_noise ? 1 : 0);
+  return launch_status("em_step_kernel");
+}
+
+int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                           const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                           const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                           const float* noise, float* traj, int32_t thin, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x_in && x_out && n > 0, "x_in/x_out must be non-null and n positive");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(step_size_host && noise_scale_host, "schedules must be non-null");
+  EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
+  EBM_CHECK_ARG(thin >= 1, "thin must be >= 1");
+  EBM_CHECK_ARG(rng_mode >= EBM_RNG_INJECTED && rng_mode <= EBM_RNG_NATIVE, "bad rng_mode");
+  EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream};
+  return langevin_dispatch(c);
+}
+
+int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, float* x_out_host, float* scratch_dev,
+                                int64_t n, int32_t n_steps, double step_size, double noise_scale, int32_t rng_mode,
+                                uint64_t seed, uint64_t offset, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x_in_host && x_out_host && scratch_dev && n > 0, "buffers must be non-null and n positive");
+  EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "host entry point draws its own noise");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)n * e->dim * sizeof(float);
+  EBM_CUDA(cudaMemcpyAsync(scratch_dev, x_in_host, bytes, cudaMemcpyHostToDevice, st));
+  rc = ebm_langevin_burst_f32(e, scratch_dev, scratch_dev, n, n_steps, &step_size, &noise_scale, 1, nullptr, rng_mode,
+                              seed, offset, nullptr, nullptr, 1, stream);
+  if (rc) return rc;
+  EBM_CUDA(cudaMemcpyAsync(x_out_host, scratch_dev, bytes, cudaMemcpyDeviceToHost, st));
+  EBM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ebm_pcd_gather_f32(const float* buffer, int64_t buffer_rows, int64_t row_elems, const int64_t* idx, int64_t batch,
+                       float* out, const int64_t* noise_rows, const float* noise, int64_t n_noise, void* stream) {
+  EBM_CHECK_ARG(buffer && idx && out, "buffer/idx/out must be non-null");
+  EBM_CHECK_ARG(buffer_rows > 0 && row_elems > 0 && batch > 0, "sizes must be positive");
+  EBM_CHECK_ARG(n_noise == 0 || (noise_rows && noise), "noise_rows/noise must be given when n_noise > 0");
+  const DeviceInfo& di = device_info(current_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  pcd_gather_kernel<<<flat_grid(di, batch * row_elems, 256), 256, 0, st>>>(buffer, row_elems, (const long long*)idx, batch, out);
+  int rc = launch_status("pcd_gather_kernel");
+  if (rc) return rc;
+  if (n_noise > 0) {
+    pcd_noise_kernel<<<flat_grid(di, n_noise * row_elems, 256), 256, 0, st>>>(out, row_elems, (const long long*)noise_rows, noise, n_noise);
+    rc = launch_status("pcd_noise_kernel");
+  }
+  return rc;
+}
+
+int ebm_pcd_scatter_f32(float* buffer, int64_t buffer_rows, int64_t row_elems, int64_t ptr, const float* samples,
+                        int64_t batch, int64_t* new_ptr_host, void* stream) {
+  EBM_CHECK_ARG(buffer && samples, "buffer/samples must be non-null");
+  EBM_CHECK_ARG(buffer_rows > 0 && row_elems > 0 && batch > 0, "sizes must be positive");
+  EBM_CHECK_ARG(ptr >= 0 && ptr < buffer_rows, "ptr out of range");
+  const DeviceInfo& di = device_info(current_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t new_ptr;
+  if (batch >= buffer_rows) {  // base_loss.py:409-413: keep the latest buffer_rows samples, ptr = 0
+    const float* src = samples + (batch - buffer_rows) * row_elems;
+    pcd_scatter_kernel<<<flat_grid(di, buffer_rows * row_elems, 256), 256, 0, st>>>(buffer, buffer_rows, row_elems, 0, src, buffer_rows);
+    new_ptr = 0;
+  } else {
+    pcd_scatter_kernel<<<flat_grid(di, batch * row_elems, 256), 256, 0, st>>>(buffer, buffer_rows, row_elems, ptr, samples, batch);
+    new_ptr = (ptr + batch) % buffer_rows;
+  }
+  if (new_ptr_host) *new_ptr_host = new_ptr;
+  return launch_status("pcd_scatter_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+"""`LangevinDynamics` and `HamiltonianMonteCarlo` with the reference's API, running fused CUDA bursts.
+
+Mirrors torchebm/core/base_sampler.py:10-155, torchebm/samplers/langevin_dynamics.py:16-188 and
+torchebm/samplers/hmc.py:19-315: same constructor and `sample()` signatures, same return shapes,
+same errors, same scheduler semantics, same RNG consumption (with `rng="torch"`, the default, a burst
+draws exactly the Philox stream the reference's per-step `randn_like` / `normal_` / `rand` calls would,
+so equal seeds give equal chains).  What differs is where the loop runs: one kernel launch does all
+`n_steps` steps (`thin` steps per launch when diagnostics are requested).
+
+Energies the library recognises (core.energy_descriptor) take the fused path.  Any other `nn.Module`
+energy keeps its own PyTorch forward/autograd for the gradient -- it is the caller's code -- and only the
+Euler-Maruyama update arithmetic runs in the library (the integrator-level boundary,
+core/base_integrator.py:673-731).  CPU tensors, non-fp32 dtypes and a missing CUDA library raise.
+"""
+
+from __future__ import annotations
+
+import warnings
+from abc import ABC, abstractmethod
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .core import BaseScheduler, EnergyDescriptor, Schedulable, TorchEBMModule, autograd_gradient, energy_descriptor
+from .integrators import (BaseSDERungeKuttaIntegrator, BaseSymplecticIntegrator, EulerMaruyamaIntegrator,
+                          LeapfrogIntegrator, resolve_integrator)
+
+
+class BaseSampler(Schedulable, TorchEBMModule, ABC):
+    """base_sampler.py:10-155."""
+
+    def __init__(self, model: nn.Module, dtype: torch.dtype = torch.float32,
+                 device: Optional[Union[str, torch.device]] = None):
+        super().__init__(device=device, dtype=dtype)
+        self.model = model
+
+    def _init_state(self, x, dim, n_samples, generator=None) -> torch.Tensor:
+        if x is not None:
+            return x.to(device=self.device, dtype=self.dtype)
+        if dim is None:
+            raise ValueError("dim must be provided when x is None")
+        shape = (dim,) if isinstance(dim, int) else tuple(dim)
+        return torch.randn(n_samples, *shape, dtype=self.dtype, device=self.device, generator=generator)
+
+    def _model_gradient(self, x, model_kwargs):
+        if model_kwargs:
+            return self.model.gradient(x, model_kwargs=model_kwargs)
+        if hasattr(self.model, "gradient"):
+            return self.model.gradient(x)
+        return autograd_gradient(self.model, x)
+
+    def _model_energy(self, x, model_kwargs):
+        if model_kwargs:
+            return self.model(x, **model_kwargs)
+        return self.model(x)
+
+    # ---- fused-path plumbing ------------------------------------------------------------------
+    def _require_cuda_fp32(self) -> None:
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                f"{type(self).__name__} runs on a CUDA device only (got device={self.device}); "
+                "torchebm_b200 has no CPU path")
+        if self.dtype != torch.float32:
+            raise TypeError(f"{type(self).__name__} supports dtype=torch.float32 only, got {self.dtype}")
+        _lib.load()
+
+    def _rng_state(self, generator: Optional[torch.Generator]) -> Tuple[torch.Generator, int, int]:
+        """(generator, seed, offset) of the Philox stream this call draws from; no host sync."""
+        if generator is None:
+            idx = ops.device_index(self.device)
+            generator = torch.cuda.default_generators[idx]
+        elif generator.device.type != "cuda":
+            raise RuntimeError(
+                f"Expected a 'cuda' device type for generator but found '{generator.device.type}'")
+        return generator, generator.initial_seed(), generator.get_offset()
+
+    def _descriptor(self, x: torch.Tensor, model_kwargs: dict) -> Optional[EnergyDescriptor]:
+        if model_kwargs or x.ndim != 2:
+            return None
+        return energy_descriptor(self.model, x.shape[1], x.device)
+
+    @abstractmethod
+    def sample(self, x=None, dim=None, n_steps=100, n_samples=1, thin=1, return_trajectory=False,
+               return_diagnostics=False, reset_schedulers=True, *, generator=None): ...
+
+
+def _batch_diag(x: torch.Tensor):
+    if x.shape[0] > 1:
+        return x.mean(dim=0), x.var(dim=0, unbiased=False).clamp_(min=1e-10, max=1e10)
+    return x.squeeze(0), torch.zeros_like(x.squeeze(0))
+
+
+class LangevinDynamics(BaseSampler):
+    """langevin_dynamics.py:16-188.  Extra keyword `rng`: "torch" (default, reference-identical stream) or
+    "native" (cheaper layout-native Philox stream)."""
+
+    def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3,
+                 noise_scale: Union[float, BaseScheduler] = 1.0, decay: float = 0.0,
+                 clamp: Optional[Tuple[float, float]] = None, dtype: torch.dtype = torch.float32,
+                 device: Optional[Union[str, torch.device]] = None,
+                 integrator: Union[str, BaseSDERungeKuttaIntegrator, None] = None, rng: str = "torch"):
+        super().__init__(model=model, dtype=dtype, device=device)
+        self._register_param("step_size", step_size, positive=True)
+        self._register_param("noise_scale", noise_scale, positive=True)
+        if clamp is not None and clamp[0] >= clamp[1]:
+            raise ValueError(f"clamp min must be < max, got {clamp}")
+        if rng not in ("torch", "native"):
+            raise ValueError("rng must be 'torch' or 'native'")
+        self.clamp = clamp
+        self.decay = decay
+        self.rng = rng
+        self.integrator = resolve_integrator(integrator, default="euler_maruyama", family=BaseSDERungeKuttaIntegrator,
+                                             owner="LangevinDynamics", device=self.device, dtype=self.dtype)
+
+    @torch.no_grad()
+    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[Union[int, Tuple[int, ...]]] = None,
+               n_steps: int = 100, n_samples: int = 1, thin: int = 1, return_trajectory: bool = False,
+               return_diagnostics: bool = False, reset_schedulers: bool = True, *,
+               model_kwargs: Optional[Dict[str, Any]] = None, generator: Optional[torch.Generator] = None):
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        self._require_cuda_fp32()
+        if reset_schedulers:
+            self.reset_schedulers()
+        gen, seed, offset = self._rng_state(generator)
+        x = self._init_state(x, dim, n_samples, generator)
+        offset = gen.get_offset()  # after _init_state, which may have drawn from the same generator
+        model_kwargs = self._prepare_model_kwargs(model_kwargs)
+        n = x.shape[0]
+        data_shape = x.shape[1:]
+        n_kept = n_steps // thin
+        desc = self._descriptor(x, model_kwargs) if type(self.integrator) is EulerMaruyamaIntegrator else None
+        if desc is None:
+            return self._sample_opaque(x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator)
+
+        x = x.contiguous()
+        rng_mode = _lib.RNG_MODES[self.rng]
+        numel = x.numel()
+        traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
+        if n_steps <= 0:
+            out = traj if return_trajectory else x
+            return (out, self._empty_diag(data_shape)) if return_diagnostics else out
+        vals, constant = self._advance_schedules(("step_size", "noise_scale"), n_steps)
+        hs, nss = vals["step_size"], vals["noise_scale"]
+
+        if not return_diagnostics:
+            out = ops.langevin_burst(desc, x, n_steps, hs, nss, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
+                                     offset=offset, traj=traj, thin=thin)
+            gen.set_offset(offset + ops.rng_consumed_langevin(self.device, numel, n_steps, rng_mode))
+            return traj if return_trajectory else out
+
+        # diagnostics: one launch per kept sample, statistics from the device-resident state
+        diag = self._empty_diag(data_shape, n_kept)
+        cur = x
+        done = 0
+        for j in range(n_kept):
+            h_j = hs if constant else hs[done:done + thin]
+            ns_j = nss if constant else nss[done:done + thin]
+            cur = ops.langevin_burst(desc, cur, thin, h_j, ns_j, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
+                                     offset=offset)
+            offset += ops.rng_consumed_langevin(self.device, numel, thin, rng_mode)
+            done += thin
+            if traj is not None:
+                traj[:, j] = cur
+            diag["mean"][j], diag["var"][j] = _batch_diag(cur)
+            diag["energy"][j] = ops.energy(desc, cur).mean()
+        rest = n_steps - done
+        if rest > 0:
+            h_j = hs if constant else hs[done:]
+            ns_j = nss if constant else nss[done:]
+            cur = ops.langevin_burst(desc, cur, rest, h_j, ns_j, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
+                                     offset=offset)
+            offset += ops.rng_consumed_langevin(self.device, numel, rest, rng_mode)
+        gen.set_offset(offset)
+        out = traj if return_trajectory else cur
+        return out, diag
+
+    def _empty_diag(self, data_shape, n_kept: int = 0):
+        return {
+            "mean": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
+            "var": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
+            "energy": torch.empty(n_kept, dtype=self.dtype, device=self.device),
+        }
+
+    def _sample_opaque(self, x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator):
+        """Energies with no library kernel: their own gradient + the integrator's fused update per step
+        (langevin_dynamics.py:157-185 verbatim in structure)."""
+        n = x.shape[0]
+        data_shape = x.shape[1:]
+        n_kept = n_steps // thin
+        traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
+        diag = self._empty_diag(data_shape, n_kept) if return_diagnostics else None
+        drift = lambda x_, t_: -self._model_gradient(x_, model_kwargs)
+        keep = 0
+        for i in range(n_steps):
+            x = self.integrator.step(state={"x": x}, step_size=self.get_scheduled_value("step_size"),
+                                     noise_scale=self.get_scheduled_value("noise_scale"), drift=drift,
+                                     generator=generator)["x"]
+            if self.clamp is not None:
+                x = x.clamp_(*self.clamp)
+            self.step_schedulers()
+            if (i + 1) % thin == 0:
+                if traj is not None:
+                    traj[:, keep] = x
+                if diag is not None:
+                    diag["mean"][keep], diag["var"][keep] = _batch_diag(x)
+                    diag["energy"][keep] = self._model_energy(x, model_kwargs).mean()
+                keep += 1
+        out = traj if return_trajectory else x
+        return (out, diag) if return_diagnostics else out
+
+
+class HamiltonianMonteCarlo(BaseSampler):
+    """hmc.py:19-315.  Extra keyword `rng` as in LangevinDynamics."""
+
+    def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3, n_leapfrog_steps: int = 10,
+                 mass: Optional[Union[float, torch.Tensor]] = None, dtype: torch.dtype = torch.float32,
+                 device: Optional[Union[str, torch.device]] = None,
+                 integrator: Union[str, BaseSymplecticIntegrator, None] = None, rng: str = "torch"):
+        super().__init__(model=model, dtype=dtype, device=device)
+        self._register_param("step_size", step_size, positive=True)
+        if n_leapfrog_steps <= 0:
+            raise ValueError("n_leapfrog_steps must be positive")
+        if rng not in ("torch", "native"):
+            raise ValueError("rng must be 'torch' or 'native'")
+        self.n_leapfrog_steps = n_leapfrog_steps
+        self.mass = mass.to(self.device) if (mass is not None and not isinstance(mass, float)) else mass
+        self.rng = rng
+        integ = resolve_integrator(integrator, default="leapfrog", family=BaseSymplecticIntegrator,
+                                   owner="HamiltonianMonteCarlo", device=self.device, dtype=self.dtype)
+        if not integ.separable:
+            raise TypeError("HamiltonianMonteCarlo requires a separable symplectic integrator")
+        self.integrator = integ
+
+    @torch.no_grad()
+    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[int] = None, n_steps: int = 100,
+               n_samples: int = 1, thin: int = 1, return_trajectory: bool = False, return_diagnostics: bool = False,
+               reset_schedulers: bool = True, *, model_kwargs: Optional[Dict[str, Any]] = None,
+               generator: Optional[torch.Generator] = None):
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        self._require_cuda_fp32()
+        if reset_schedulers:
+            self.reset_schedulers()
+        model_kwargs = self._prepare_model_kwargs(model_kwargs)
+        if x is None and dim is None:
+            if hasattr(self.model, "mean") and isinstance(self.model.mean, torch.Tensor):
+                dim = self.model.mean.shape[0]
+            else:
+                raise ValueError("dim must be provided when x is None and cannot be inferred from model")
+        gen, seed, _ = self._rng_state(generator)
+        x = self._init_state(x, dim, n_samples, generator)
+        offset = gen.get_offset()
+        if x.ndim != 2:
+            raise ValueError(f"HamiltonianMonteCarlo expects a 2-D state [n_samples, dim], got {tuple(x.shape)}")
+        n, d = x.shape
+        n_kept = n_steps // thin
+        desc = self._descriptor(x, model_kwargs) if type(self.integrator) is LeapfrogIntegrator else None
+        if desc is None or desc.kind == "mlp":
+            raise _lib.EbmUnsupported(
+                f"HamiltonianMonteCarlo has fused kernels for the analytic energies only; "
+                f"{type(self.model).__name__} is not one of them")
+        x = x.contiguous()
+        rng_mode = _lib.RNG_MODES[self.rng]
+        traj = torch.empty((n, n_kept, d), dtype=self.dtype, device=self.device) if return_trajectory else None
+        diag = None
+        if return_diagnostics:
+            diag = {k: torch.empty(n_kept, d, dtype=self.dtype, device=self.device) for k in ("mean", "var")}
+            diag["energy"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
+            diag["acceptance_rate"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
+        if n_steps <= 0:
+            out = traj if return_trajectory else x
+            return (out, diag) if return_diagnostics else out
+        vals, constant = self._advance_schedules(("step_size",), n_steps)
+        hs = vals["step_size"]
+
+        if not return_diagnostics:
+            out = ops.hmc_burst(desc, x, n_steps, self.n_leapfrog_steps, hs, mass=self.mass, rng_mode=rng_mode,
+                                seed=seed, offset=offset, traj=traj, thin=thin)
+            gen.set_offset(offset + ops.rng_consumed_hmc(self.device, n, d, n_steps, rng_mode))
+            return traj if return_trajectory else out
+
+        cur = x
+        done = 0
+        acc = torch.zeros(n_steps, dtype=torch.int32, device=self.device)
+        e_out = torch.empty(n, dtype=self.dtype, device=self.device)
+        for j in range(n_kept):
+            h_j = hs if constant else hs[done:done + thin]
+            cur = ops.hmc_burst(desc, cur, thin, self.n_leapfrog_steps, h_j, mass=self.mass, rng_mode=rng_mode,
+                                seed=seed, offset=offset, accept_count=acc[done:done + thin], energy_out=e_out)
+            offset += ops.rng_consumed_hmc(self.device, n, d, thin, rng_mode)
+            done += thin
+            if traj is not None:
+                traj[:, j, :] = cur
+            diag["mean"][j] = cur.mean(dim=0)
+            diag["var"][j] = (cur.var(dim=0, unbiased=False).clamp_(min=1e-10, max=1e10) if n > 1
+                              else torch.zeros(d, dtype=self.dtype, device=self.device))
+            diag["energy"][j] = e_out.mean()
+            diag["acceptance_rate"][j] = acc[done - 1].to(self.dtype) / n
+        rest = n_steps - done
+        if rest > 0:
+            h_j = hs if constant else hs[done:]
+            cur = ops.hmc_burst(desc, cur, rest, self.n_leapfrog_steps, h_j, mass=self.mass, rng_mode=rng_mode,
+                                seed=seed, offset=offset)
+            offset += ops.rng_consumed_hmc(self.device, n, d, rest, rng_mode)
+        gen.set_offset(offset)
+        out = traj if return_trajectory else cur
+        return out, diag
