@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the fused MCMC negative-sampling hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|mlp128|c4]
+
+One bench "step" = one pass of the hot path over one batch: a K-step fused burst through the sampler-level
+API (`ops.langevin_burst` / `ops.hmc_burst`, i.e. one C-ABI call, one kernel launch).  Headline workload =
+BASELINE.json configs[1] ("c2"): LangevinDynamics on DoubleWell, dim 128, 65 536 chains, k = 500.
+Metric = Langevin chain-steps per second (n_chains x k_steps / wall), whole job over all GPUs.
+
+N > 1 (torchrun, one rank per GPU, NCCL): the chain axis is sharded (strong scaling: 65 536 chains in total),
+each rank runs its burst with no communication and the step ends with ONE all-gather of the [N/W, D] shards.
+
+`--impl reference`: the reference's CPU path (oracle = op-for-op restatement of torchebm's PyTorch sampler,
+autograd gradient included) on the host cores, on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, n_chains, dim, k)
+    "c2": ("LangevinDynamics DoubleWell(2.0,1.0) dim=128 n_chains=65536 k=500 step_size=0.01 noise_scale=1.0", 65536, 128, 500),
+    "mlp128": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01", 65536, 128, 100),
+    "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
+}
+METRIC = "langevin_chain_steps_per_sec"
+UNIT = "chain-steps/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def make_workload(name: str, n_local: int, dev):
+    """Returns (step_fn(x_in, out, seed_offset) -> launches, desc, algorithmic bytes per chain-step, units per step)."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    _, _, d, k = WORKLOADS[name]
+    if name == "c2":
+        model = te.DoubleWellModel(2.0, 1.0)
+        desc = te.energy_descriptor(model, d, dev)
+        inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
+
+        def step(x, out, it):
+            ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            return 1
+
+        return step, desc, model, 8 * d, k
+    if name == "mlp128":
+        torch.manual_seed(0)
+        model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev)
+        desc = te.energy_descriptor(model, d, dev)
+        inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_NATIVE)
+
+        def step(x, out, it):
+            ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=1234, offset=it * inc, out=out)
+            return 1
+
+        return step, desc, model, 8 * d, k
+    if name == "c4":
+        model = te.RastriginModel(10.0)
+        desc = te.energy_descriptor(model, d, dev)
+        inc = ops.rng_consumed_hmc(dev, n_local, d, 1, _lib.RNG_TORCH)
+
+        def step(x, out, it):
+            ops.hmc_burst(desc, x, 1, k, [0.01], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            return 1
+
+        return step, desc, model, 16 * d, k
+    raise KeyError(name)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import torchebm_b200 as te  # noqa: F401
+    from torchebm_b200 import _lib, ops
+    from torchebm_b200.distributed import gather_chains, shard_bounds
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    desc_text, n_total, d, k = WORKLOADS[args.workload]
+    lo, hi = shard_bounds(n_total, rank, world)
+    n_local = hi - lo
+    step, desc, model, bytes_per_unit, units_per_chain = make_workload(args.workload, n_local, dev)
+
+    # synthetic particle batch: N(0,1) truncated to +-3 so every chain starts inside the stability region of the
+    # explicit step (|x| < 5 at h = 0.01 for DoubleWell); the reference diverges to NaN outside it as well
+    x_full = torch.randn(n_total, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
+    x_local = x_full[lo:hi].to(dev)
+    out_local = torch.empty_like(x_local)
+    gathered = torch.empty(n_total, d, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(it):
+        n = step(x_local, out_local, it)
+        if world > 1:
+            gather_chains(out_local, out=gathered)
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(args.warmup):
+        one_step(it)
+    barrier()
+
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kstarts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches = 0
+    with ClockSampler(local) as clocks:
+        barrier()
+        for it in range(args.steps):
+            flush.zero_()  # evict the state from L2 between timed iterations (not timed)
+            starts[it].record()
+            kstarts[it].record()
+            launches += step(x_local, out_local, args.warmup + it)
+            kends[it].record()
+            if world > 1:
+                gather_chains(out_local, out=gathered)
+            ends[it].record()
+        barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    kernel_ms = sum(s.elapsed_time(e) for s, e in zip(kstarts, kends))
+    if world > 1:
+        t = torch.tensor([total_ms, kernel_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kernel_ms = t.tolist()
+        launches_t = torch.tensor([launches], device=dev)
+        dist.all_reduce(launches_t)
+        launches = int(launches_t.item())
+    ms_per_step = total_ms / args.steps
+    units = n_total * units_per_chain  # chain-steps (or leapfrog chain-steps) per bench step, whole job
+    value = units / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if args.workload == "c2":
+        xh = x_full[lo:hi].contiguous().pin_memory()
+        oh = torch.empty_like(xh).pin_memory()
+        scratch = torch.empty_like(x_local)
+        inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
+        for it in range(max(1, args.warmup)):
+            ops.langevin_burst_host(desc, xh, oh, scratch, k, 0.01, 1.0, _lib.RNG_TORCH, 1234, it * inc)
+        barrier()
+        t0s, t1s = [], []
+        for it in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.langevin_burst_host(desc, xh, oh, scratch, k, 0.01, 1.0, _lib.RNG_TORCH, 1234, it * inc)
+            b.record()
+            t0s.append(a)
+            t1s.append(b)
+        barrier()
+        e2e_ms = sum(a.elapsed_time(b) for a, b in zip(t0s, t1s))
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = t.item()
+        e2e = {"value": units / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": n_total * d * 4, "d2h_bytes_per_step": n_total * d * 4,
+               "api": "ebm_langevin_burst_host_f32 (pinned host in/out, synchronised per call)"}
+
+    if rank != 0:
+        return
+    peaks, peak_kind = measured_peaks()
+    algo_bytes_per_launch = bytes_per_unit * (n_local * units_per_chain)
+    kernel_s = kernel_ms / args.steps * 1e-3
+    achieved = algo_bytes_per_launch / kernel_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload)
+    line = {
+        "metric": METRIC if args.workload != "c4" else "hmc_leapfrog_chain_steps_per_sec",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc_text, "rng": "torch-layout Philox4x32-10 drawn in-kernel",
+                   "chains_per_gpu": n_local, "collective": "all_gather of [N/W, D] shards at burst end" if world > 1 else "none",
+                   "l2": "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events"},
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind + " (burst copy)",
+                     "algorithmic_bytes_per_launch": algo_bytes_per_launch,
+                     "kernel_ms": kernel_ms / args.steps,
+                     "note": "SURVEY 8(d) streaming model: 8*D bytes per chain-step (16*D per HMC leapfrog step); the burst "
+                             "keeps the chain in registers, so real DRAM traffic is 8*D*N bytes per BURST and the kernel is "
+                             "instruction-issue bound; see DESIGN.md and profiles/"},
+    }
+    if args.workload == "c2" and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=args.cpu_k)
+        line["torch_cuda_baseline"] = torch_cuda_baseline(dev)
+    print(json.dumps(line))
+
+
+def _oracle_energy(workload):
+    from oracle import energies as E
+
+    return E.DoubleWell(2.0, 1.0)
+
+
+def cpu_baseline(workload: str, k_sample: int, repeats: int = 1):
+    """The reference's CPU path (oracle port: same torch ops, autograd gradient per step) on the host cores."""
+    from oracle import langevin as olang
+
+    _, n, d, k = WORKLOADS[workload]
+    x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
+    gen = torch.Generator().manual_seed(1)
+    en = _oracle_energy(workload)
+    olang.sample(en, x0, 1, 0.01, 1.0, generator=gen)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        olang.sample(en, x0, k_sample, 0.01, 1.0, generator=gen)
+    dt = (time.perf_counter() - t0) / repeats
+    return {"value": n * k_sample / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n}x{d} chains, {k_sample} of the {k} steps (per-step cost is constant in the reference loop)",
+            "host_cpus": os.cpu_count(), "seconds": dt}
+
+
+def torch_cuda_baseline(dev, k_sample: int = 20):
+    """Same torch-op restatement of the reference run on the GPU: the 'reference PyTorch-CUDA' denominator of north_star."""
+    from oracle import langevin as olang
+
+    _, n, d, k = WORKLOADS["c2"]
+    x0 = torch.randn(n, d, device=dev).clamp_(-3.0, 3.0)
+    gen = torch.Generator(dev).manual_seed(1)
+    en = _oracle_energy("c2")
+    olang.sample(en, x0, 3, 0.01, 1.0, generator=gen)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    olang.sample(en, x0, k_sample, 0.01, 1.0, generator=gen)
+    b.record()
+    torch.cuda.synchronize()
+    return {"value": n * k_sample / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
+            "what": "oracle (op-for-op restatement of the reference sampler, autograd gradient) on the same GPU",
+            "sample": f"{n}x{d} chains, {k_sample} steps"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc_text, n, d, k = WORKLOADS["c2"]
+    from oracle import langevin as olang
+
+    en = _oracle_energy("c2")
+    x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
+    gen = torch.Generator().manual_seed(1)
+    ks = args.cpu_k
+    for _ in range(args.warmup):
+        olang.sample(en, x0, ks, 0.01, 1.0, generator=gen)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        olang.sample(en, x0, ks, 0.01, 1.0, generator=gen)
+    dt = time.perf_counter() - t0
+    value = n * ks * args.steps / dt
+    sample = f"each step = {n}x{d} chains, {ks} of the {k} Langevin steps on the host cores"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc_text, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-k", type=int, default=5, help="Langevin steps per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

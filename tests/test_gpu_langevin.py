@@ -234,7 +234,7 @@ def test_scheduled_burst_longer_than_one_table_chunk():
     hs = te.ExponentialDecayScheduler(start_value=0.02, decay_rate=0.99, min_value=0.001)
     nss = te.LinearScheduler(start_value=1.0, end_value=0.2, n_steps=k)
     sampler = te.LangevinDynamics(te.DoubleWellModel(), step_size=hs, noise_scale=nss, device=DEV)
-    x0 = torch.randn(512, 8, device=DEV)
+    x0 = torch.randn(512, 8, device=DEV).clamp_(-2.0, 2.0)  # keep the explicit Euler step in its stable region
     got, diag = sampler.sample(x=x0, n_steps=k, thin=7, return_trajectory=True, return_diagnostics=True,
                                generator=torch.Generator(DEV).manual_seed(4))
     assert hs.step_count == k and nss.step_count == k
@@ -295,7 +295,9 @@ def test_full_size_c2_properties():
     import torchebm_b200 as te
 
     sampler = te.LangevinDynamics(te.DoubleWellModel(2.0, 1.0), step_size=0.01, noise_scale=1.0, device=DEV)
-    x0 = torch.randn(65536, 128, device=DEV, generator=torch.Generator(DEV).manual_seed(0))
+    # |x| > 5 is outside the stability region of the explicit step at h = 0.01 (the reference diverges there
+    # too), and 8.4M normal draws do reach it: truncate the synthetic start like bench.py does
+    x0 = torch.randn(65536, 128, device=DEV, generator=torch.Generator(DEV).manual_seed(0)).clamp_(-3.0, 3.0)
     a = sampler.sample(x=x0, n_steps=500, generator=torch.Generator(DEV).manual_seed(1))
     b = sampler.sample(x=x0, n_steps=500, generator=torch.Generator(DEV).manual_seed(1))
     assert torch.equal(a, b)
