@@ -289,15 +289,17 @@ def run_ours(args):
                              "keeps the chain in registers, so real DRAM traffic is 8*D*N bytes per BURST and the kernel is "
                              "instruction-issue bound; see DESIGN.md and profiles/"},
     }
-    if args.workload == "c2" and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=args.cpu_k)
-        line["torch_cuda_baseline"] = torch_cuda_baseline(dev)
+    if args.workload in ("c2", "mlp128") and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=args.cpu_k if args.workload == "c2" else 2)
+        line["torch_cuda_baseline"] = torch_cuda_baseline(dev, args.workload)
     print(json.dumps(line))
 
 
-def _oracle_energy(workload):
+def _oracle_energy(workload, device="cpu"):
     from oracle import energies as E
 
+    if workload == "mlp128":
+        return E.make_mlp(128, (128, 128), "silu", seed=0).to(device)
     return E.DoubleWell(2.0, 1.0)
 
 
@@ -319,14 +321,14 @@ def cpu_baseline(workload: str, k_sample: int, repeats: int = 1):
             "host_cpus": os.cpu_count(), "seconds": dt}
 
 
-def torch_cuda_baseline(dev, k_sample: int = 20):
+def torch_cuda_baseline(dev, workload: str = "c2", k_sample: int = 20):
     """Same torch-op restatement of the reference run on the GPU: the 'reference PyTorch-CUDA' denominator of north_star."""
     from oracle import langevin as olang
 
-    _, n, d, k = WORKLOADS["c2"]
+    _, n, d, k = WORKLOADS[workload]
     x0 = torch.randn(n, d, device=dev).clamp_(-3.0, 3.0)
     gen = torch.Generator(dev).manual_seed(1)
-    en = _oracle_energy("c2")
+    en = _oracle_energy(workload, dev)
     olang.sample(en, x0, 3, 0.01, 1.0, generator=gen)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
