@@ -398,6 +398,8 @@ def _match_mlp(net) -> Optional[Tuple[nn.Linear, nn.Linear, nn.Linear, int]]:
 # --------------------------------------------------------------------------------------------------
 # descriptor extraction
 
+MLP_MAX_WIDTH = 128  # kMlpMax of csrc/ebm_mlp.cu
+
 
 class EnergyDescriptor:
     """An `EbmEnergyDesc` plus the tensors that keep its device pointers alive."""
@@ -472,6 +474,8 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         l1, l2, l3, act = m
         if l1.in_features != dim:
             return None
+        if max(l1.in_features, l1.out_features, l2.out_features) > MLP_MAX_WIDTH:
+            return None  # no fused kernel yet: integrator-level path (own autograd + fused update)
         ts = [_dev_f32(t, device) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight.reshape(-1), l3.bias)]
         d.kind = _lib.ENERGY_MLP
         d.hidden1, d.hidden2, d.activation = l1.out_features, l2.out_features, act
