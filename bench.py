@@ -35,6 +35,8 @@ WORKLOADS = {
     # name: (description, n_chains, dim, k)
     "c2": ("LangevinDynamics DoubleWell(2.0,1.0) dim=128 n_chains=65536 k=500 step_size=0.01 noise_scale=1.0", 65536, 128, 500),
     "mlp128": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01", 65536, 128, 100),
+    "mlp128_fp32": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (fp32 FFMA kernel)", 65536, 128, 100),
+    "mlp128_bf16": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (single-pass bf16)", 65536, 128, 100),
     "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
 }
 METRIC = "langevin_chain_steps_per_sec"
@@ -137,9 +139,10 @@ def make_workload(name: str, n_local: int, dev):
             return 1
 
         return step, desc, model, 8 * d, k
-    if name == "mlp128":
+    if name.startswith("mlp128"):
         torch.manual_seed(0)
-        model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev)
+        prec = {"mlp128": "bf16x3", "mlp128_fp32": "fp32", "mlp128_bf16": "bf16"}[name]
+        model = te.MLPEnergy(dim=d, hidden=128, activation="silu", precision=prec).to(dev)
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_NATIVE)
 
@@ -298,7 +301,7 @@ def run_ours(args):
 def _oracle_energy(workload, device="cpu"):
     from oracle import energies as E
 
-    if workload == "mlp128":
+    if workload.startswith("mlp128"):
         return E.make_mlp(128, (128, 128), "silu", seed=0).to(device)
     return E.DoubleWell(2.0, 1.0)
 

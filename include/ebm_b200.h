@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 1
+#define EBM_ABI_VERSION 2
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -49,6 +49,13 @@ enum { EBM_RNG_INJECTED = 0, EBM_RNG_TORCH = 1, EBM_RNG_NATIVE = 2 };
 
 enum { EBM_MASS_NONE = 0, EBM_MASS_SCALAR = 1, EBM_MASS_VECTOR = 2 };
 
+/* Arithmetic of the MLP-energy products.
+ *   FP32  : fp32 FFMA on the CUDA cores (summation order differs from cuBLAS, ~1e-6 relative).
+ *   BF16X3: tcgen05 tensor cores, every operand split into bf16 hi + lo, hi*hi + lo*hi + hi*lo accumulated in fp32
+ *           tensor memory (~2e-5 relative); the default of the Python samplers.
+ *   BF16  : tcgen05 tensor cores, single bf16 pass (~4e-3 relative). */
+enum { EBM_MLP_FP32 = 0, EBM_MLP_BF16X3 = 1, EBM_MLP_BF16 = 2 };
+
 typedef struct EbmEnergyDesc {
   int32_t kind;         /* EBM_ENERGY_* */
   int32_t dim;          /* D */
@@ -56,6 +63,8 @@ typedef struct EbmEnergyDesc {
   int32_t hidden1;      /* MLP: H1 */
   int32_t hidden2;      /* MLP: H2 */
   int32_t activation;   /* MLP: EBM_ACT_* */
+  int32_t precision;    /* MLP: EBM_MLP_* (Langevin burst only; energy/gradient evaluation is always FP32) */
+  int32_t reserved;
   /* scalar parameters (fp32, already rounded the way torch rounds the Python doubles):
    *   DoubleWell: p[0] = barrier_height, p[1] = b*b
    *   Harmonic  : p[0] = 0.5*k

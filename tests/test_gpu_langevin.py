@@ -184,6 +184,51 @@ def test_same_seed_matches_reference_stream_on_cuda(name, n, d, k):
     torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("precision,rtol,atol", [("fp32", 1e-4, 2e-5), ("bf16x3", 1e-4, 2e-5), ("bf16", 5e-2, 5e-3)])
+@pytest.mark.parametrize("name", ["langevin_mlp_silu", "langevin_mlp_tanh", "langevin_mlp_d128"])
+def test_mlp_precisions_match_reference_golden(name, precision, rtol, atol):
+    """fp32 = CUDA-core FFMA kernel; bf16x3 / bf16 = tcgen05 tensor-core kernel (split operands / single pass)."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    g = C.load(name)
+    model = _model_for(name, g)
+    model.precision = precision
+    x0 = g["x0"].to(DEV)
+    desc = te.energy_descriptor(model, x0.shape[1], x0.device)
+    assert desc.c.precision == _lib.MLP_PRECISIONS[precision]
+    noise = C.langevin_noise(g).to(DEV)
+    out = ops.langevin_burst(desc, x0, int(g["k"]), [float(g["h"])], [float(g["ns"])], rng_mode=_lib.RNG_INJECTED, noise=noise)
+    torch.testing.assert_close(out.cpu(), g["out"], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_mlp_tensor_core_kernel_many_tiles_trajectory_and_native_rng(precision):
+    """More tiles than SMs (persistent loop), ragged last tile, trajectory + clamp, native and torch RNG."""
+    import torchebm_b200 as te
+
+    torch.manual_seed(0)
+    model = te.MLPEnergy(dim=100, hidden=(128, 96), activation="silu", precision=precision).to(DEV)
+    lin = [l for l in model.net if isinstance(l, torch.nn.Linear)]
+    en = E.MLP([l.weight for l in lin], [l.bias for l in lin], "silu")
+    n = 148 * 128 * 2 + 77
+    x0 = torch.randn(n, 100, device=DEV).clamp_(-3, 3)
+    s = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, clamp=(-2.5, 2.5), device=DEV)
+    got = s.sample(x=x0, n_steps=6, thin=2, return_trajectory=True, generator=torch.Generator(DEV).manual_seed(9))
+    want = olang.sample(en, x0, 6, 0.01, 0.5, clamp=(-2.5, 2.5), thin=2, return_trajectory=True,
+                        generator=torch.Generator(DEV).manual_seed(9))
+    assert got.shape == (n, 3, 100)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
+    sn = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, device=DEV, rng="native")
+    a = sn.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(1))
+    b = sn.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(1))
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    # native stream is layout independent: the fp32 and tensor-core kernels draw the same noise
+    model.precision = "fp32" if precision == "bf16x3" else "bf16x3"
+    c = sn.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(1))
+    torch.testing.assert_close(a, c, rtol=1e-4, atol=2e-5)
+
+
 def test_x_none_draws_initial_state_from_generator():
     import torchebm_b200 as te
 

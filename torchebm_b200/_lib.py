@@ -13,12 +13,14 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libebm_b200.so")
 
-EBM_ABI_VERSION = 1
+EBM_ABI_VERSION = 2
 
 ENERGY_DOUBLE_WELL, ENERGY_HARMONIC, ENERGY_RASTRIGIN, ENERGY_GAUSSIAN, ENERGY_MOG, ENERGY_MLP = range(6)
 ACT_SILU, ACT_TANH, ACT_RELU, ACT_SOFTPLUS = range(4)
 RNG_INJECTED, RNG_TORCH, RNG_NATIVE = range(3)
 MASS_NONE, MASS_SCALAR, MASS_VECTOR = range(3)
+MLP_FP32, MLP_BF16X3, MLP_BF16 = range(3)
+MLP_PRECISIONS = {"fp32": MLP_FP32, "bf16x3": MLP_BF16X3, "bf16": MLP_BF16}
 ERR_INVALID, ERR_UNSUPPORTED = -1, -2
 
 RNG_MODES = {"injected": RNG_INJECTED, "torch": RNG_TORCH, "native": RNG_NATIVE}
@@ -32,6 +34,8 @@ class EbmEnergyDesc(C.Structure):
         ("hidden1", C.c_int32),
         ("hidden2", C.c_int32),
         ("activation", C.c_int32),
+        ("precision", C.c_int32),
+        ("reserved", C.c_int32),
         ("p", C.c_float * 4),
         ("buf", C.c_void_p * 8),
     ]

@@ -362,8 +362,13 @@ class MLPEnergy(BaseModel):
     Pass an existing `nn.Sequential` as `net` to share its parameters."""
 
     def __init__(self, dim: Optional[int] = None, hidden: Union[int, Sequence[int]] = 128, activation: str = "silu",
-                 net: Optional[nn.Sequential] = None, *args, **kwargs):
+                 net: Optional[nn.Sequential] = None, precision: str = "bf16x3", *args, **kwargs):
         super().__init__(*args, **kwargs)
+        if precision not in _lib.MLP_PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.MLP_PRECISIONS)}")
+        #: arithmetic of the fused Langevin products: "bf16x3" (tensor cores, split operands, ~2e-5 relative),
+        #: "fp32" (CUDA cores) or "bf16" (tensor cores, single pass, ~4e-3 relative)
+        self.precision = precision
         if net is None:
             if dim is None:
                 raise ValueError("dim must be given when net is None")
@@ -479,6 +484,7 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         ts = [_dev_f32(t, device) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight.reshape(-1), l3.bias)]
         d.kind = _lib.ENERGY_MLP
         d.hidden1, d.hidden2, d.activation = l1.out_features, l2.out_features, act
+        d.precision = _lib.MLP_PRECISIONS[getattr(model, "precision", "bf16x3")]
         for i, t in enumerate(ts):
             d.buf[i] = t.data_ptr()
         return EnergyDescriptor(d, ts, "mlp")

@@ -402,7 +402,12 @@ int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, 
   return launch_status("mlp_energy_grad_kernel");
 }
 
+int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes);  // ebm_mlp_tc.cu
+
 int langevin_mlp_dispatch(const LangevinCall& c) {
+  if (c.e->precision == EBM_MLP_BF16X3) return langevin_mlp_tc_dispatch(c, 3);
+  if (c.e->precision == EBM_MLP_BF16) return langevin_mlp_tc_dispatch(c, 1);
+  if (c.e->precision != EBM_MLP_FP32) { set_error("bad MLP precision %d", c.e->precision); return EBM_ERR_INVALID; }
   MlpParams P;
   int rc = fill_mlp(c.e, P);
   if (rc) return rc;

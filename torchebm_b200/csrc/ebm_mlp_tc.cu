@@ -1,0 +1,422 @@
+// MLP-energy Langevin burst on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Same math as ebm_mlp.cu (E = w3 . act(W2 act(W1 x + b1) + b2) + b3, grad = W1^T(act'(z1) * (W2^T(act'(z2) * w3))))
+// with the four [128 x 128 x 128] products per Langevin step issued as tcgen05.mma (kind::f16, bf16 operands, fp32
+// accumulators in tensor memory).  fp32-grade accuracy comes from split operands: every operand v is stored as
+// hi = bf16(v), lo = bf16(v - hi) and each product is accumulated as hi*hi + lo*hi + hi*lo (error ~2^-16 relative to
+// the largest term; the dropped lo*lo term is ~2^-18).  precision == EBM_MLP_BF16 skips the two correction passes.
+//
+// One CTA = one tile of 128 chains (TMEM lane = chain), persistent over tiles, resident for all K steps:
+//   warp 0      : allocates TMEM, then one elected lane issues every MMA and commits to an mbarrier;
+//   warps 1..8  : epilogue.  Thread = (row r = TMEM lane, column half); x[r, 64 cols] lives in its registers.
+// Per step and tile the dependency chain is GEMM1 -> E1 -> GEMM2 -> E2 -> GEMM3 -> E3 -> GEMM4 -> E4(update) -> GEMM1'.
+// Each epilogue produces the A operand of the NEXT product in 16-column chunks (= one MMA k-step) and signals a
+// per-chunk mbarrier, so the MMA of product n+1 runs underneath epilogue n; the tensor pipe is hidden behind the
+// CUDA-core work (activations, Philox, operand splitting), which is the real bound of this kernel.
+//   TMEM columns: [0,128) acc0, [128,256) acc1 (products alternate), [256,384) act'(z1) kept for E3.
+//   SMEM: W1/W2 hi+lo in the no-swizzle core-matrix layout of umma.cuh (one copy serves the K-major forward and the
+//   MN-major backward descriptor), A hi+lo operand buffer, biases, barriers: 198 KB.
+#include "api_common.cuh"
+#include "umma.cuh"
+#include <cuda_bf16.h>
+
+namespace ebm {
+
+using namespace umma;
+
+constexpr int kTcM = 128;          // chains per tile = TMEM lanes
+constexpr int kTcW = 128;          // padded width of every layer
+constexpr int kTcChunks = kTcW / 16;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = 32 * (1 + kTcEpiWarps);
+constexpr int kTcMatBytes = kTcW * kTcW * 2;  // one bf16 [128 x 128] operand
+
+struct TcParams {
+  const float* W1; const float* b1; const float* W2; const float* b2; const float* w3;
+  int d, h1, h2;
+  int passes;  // 3: bf16x3 split, 1: plain bf16
+  const float* x_in;
+  float* x_out;
+  const float* noise;
+  float* traj;
+  long long n;
+  int n_steps, thin, n_kept, thin_start, kept_base, has_clamp;
+  float clamp_lo, clamp_hi;
+  RowRng rng;
+};
+
+struct TcSmemLayout {
+  static constexpr int w1_hi = 0;
+  static constexpr int w1_lo = w1_hi + kTcMatBytes;
+  static constexpr int w2_hi = w1_lo + kTcMatBytes;
+  static constexpr int w2_lo = w2_hi + kTcMatBytes;
+  static constexpr int a_hi = w2_lo + kTcMatBytes;
+  static constexpr int a_lo = a_hi + kTcMatBytes;
+  static constexpr int b1 = a_lo + kTcMatBytes;
+  static constexpr int b2 = b1 + kTcW * 4;
+  static constexpr int w3 = b2 + kTcW * 4;
+  static constexpr int bars = w3 + kTcW * 4;           // kTcChunks + 1 mbarriers
+  static constexpr int tmem_slot = bars + (kTcChunks + 1) * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// write 16 consecutive columns [col0, col0+16) of row r of the A operand (hi and lo copies)
+__device__ __forceinline__ void store_a_chunk(uint8_t* smem, int r, int col0, const float (&v)[16], bool with_lo) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[half * 8 + 2 * j], h0, l0);
+      split_bf16(v[half * 8 + 2 * j + 1], h1, l1);
+      ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const int off = core_offset(r, col0 + half * 8, kTcM);
+    *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// all lanes of the warp have written their rows of one chunk: publish it to the MMA warp
+__device__ __forceinline__ void signal_chunk(uint8_t* smem, int chunk, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(smem_u32(smem + TcSmemLayout::bars + chunk * 8));
+}
+
+template <int ACT>
+__device__ __forceinline__ void act_fast(float z, float& h, float& dh) {
+  if (ACT == EBM_ACT_SILU) {
+    const float s = __frcp_rn(1.0f + __expf(-z));
+    h = z * s;
+    dh = s * (1.0f + z * (1.0f - s));
+  } else if (ACT == EBM_ACT_TANH) {
+    const float e = __expf(-2.0f * fabsf(z));
+    const float t = copysignf((1.0f - e) * __frcp_rn(1.0f + e), z);
+    h = t;
+    dh = 1.0f - t * t;
+  } else if (ACT == EBM_ACT_RELU) {
+    h = z > 0.0f ? z : 0.0f;
+    dh = z > 0.0f ? 1.0f : 0.0f;
+  } else {
+    h = z > 20.0f ? z : log1pf(__expf(z));
+    dh = __frcp_rn(1.0f + __expf(-z));
+  }
+}
+
+__device__ void tc_stage_weights(uint8_t* smem, const TcParams& P) {
+  for (int i = threadIdx.x; i < kTcW * kTcW; i += blockDim.x) {
+    const int r = i / kTcW, c = i - r * kTcW;
+    __nv_bfloat16 hi, lo;
+    split_bf16((r < P.h1 && c < P.d) ? P.W1[r * P.d + c] : 0.0f, hi, lo);
+    const int off = core_offset(r, c, kTcW);
+    *reinterpret_cast<__nv_bfloat16*>(smem + TcSmemLayout::w1_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(smem + TcSmemLayout::w1_lo + off) = lo;
+    split_bf16((r < P.h2 && c < P.h1) ? P.W2[r * P.h1 + c] : 0.0f, hi, lo);
+    *reinterpret_cast<__nv_bfloat16*>(smem + TcSmemLayout::w2_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(smem + TcSmemLayout::w2_lo + off) = lo;
+  }
+  float* b1 = reinterpret_cast<float*>(smem + TcSmemLayout::b1);
+  float* b2 = reinterpret_cast<float*>(smem + TcSmemLayout::b2);
+  float* w3 = reinterpret_cast<float*>(smem + TcSmemLayout::w3);
+  for (int i = threadIdx.x; i < kTcW; i += blockDim.x) {
+    b1[i] = i < P.h1 ? P.b1[i] : 0.0f;
+    b2[i] = i < P.h2 ? P.b2[i] : 0.0f;
+    w3[i] = i < P.h2 ? P.w3[i] : 0.0f;
+  }
+}
+
+// one product: D[tmem_d] = A (k-major, chunks published by the epilogue) x B, B = W^T (forward) or W (backward)
+__device__ __forceinline__ void tc_issue_gemm(uint8_t* smem, uint32_t tmem_d, int w_hi_off, int w_lo_off, bool backward,
+                                              int ksteps, int passes, uint32_t parity) {
+  const uint32_t a_hi = smem_u32(smem + TcSmemLayout::a_hi), a_lo = smem_u32(smem + TcSmemLayout::a_lo);
+  const uint32_t w_hi = smem_u32(smem + w_hi_off), w_lo = smem_u32(smem + w_lo_off);
+  const uint32_t idesc = make_idesc_bf16(kTcM, kTcW, backward);
+  for (int c = 0; c < ksteps; ++c) {
+    mbar_wait(smem_u32(smem + TcSmemLayout::bars + c * 8), parity);
+    tcgen05_fence_after();
+    const uint32_t a_off = c * 2 * (kTcM * 16);
+    // forward: B K-major (rows = outputs): next k-step = 2 core columns; backward: B MN-major: next k-step = 16 rows
+    const uint32_t b_off = backward ? c * 256 : c * 2 * (kTcW * 16);
+    const uint32_t b_lbo = backward ? 128 : kTcW * 16, b_sbo = backward ? kTcW * 16 : 128;
+    const uint64_t ah = make_smem_desc(a_hi + a_off, kTcM * 16, 128);
+    const uint64_t bh = make_smem_desc(w_hi + b_off, b_lbo, b_sbo);
+    mma_bf16(tmem_d, ah, bh, idesc, c > 0);
+    if (passes == 3) {
+      const uint64_t al = make_smem_desc(a_lo + a_off, kTcM * 16, 128);
+      const uint64_t bl = make_smem_desc(w_lo + b_off, b_lbo, b_sbo);
+      mma_bf16(tmem_d, al, bh, idesc, true);
+      mma_bf16(tmem_d, ah, bl, idesc, true);
+    }
+  }
+  mma_commit(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8));
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __grid_constant__ TcParams P,
+                                                                        const __grid_constant__ StepTable tab) {
+  extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  tc_stage_weights(smem, P);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < kTcChunks; ++c) mbar_init(smem_u32(smem + TcSmemLayout::bars + c * 8), 4);  // 4 warps per chunk
+    mbar_init(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(smem + TcSmemLayout::tmem_slot), 512);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + TcSmemLayout::tmem_slot);
+  const long long n_tiles = (P.n + kTcM - 1) / kTcM;
+  const int k1 = (P.d + 15) / 16, k2 = (P.h1 + 15) / 16, k3 = (P.h2 + 15) / 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t parity = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int k = 0; k < P.n_steps; ++k) {
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity); parity ^= 1;
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps -------------------------------------------------------------------------
+    const int e = warp - 1;
+    const int row = 32 * (warp & 3) + lane;        // TMEM lane this thread may access
+    const int ch = e >> 2;                          // column half
+    const int col_base = 64 * ch;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const float* b1 = reinterpret_cast<const float*>(smem + TcSmemLayout::b1);
+    const float* b2 = reinterpret_cast<const float*>(smem + TcSmemLayout::b2);
+    const float* w3 = reinterpret_cast<const float*>(smem + TcSmemLayout::w3);
+    const uint32_t acc_bar = smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8);
+    const bool with_lo = P.passes == 3;
+    const long long numel = P.n * P.d;
+    const bool quad_rng = (P.d % 4 == 0);
+    uint32_t parity = 0;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long grow = tile * kTcM + row;
+      const bool rv = grow < P.n;
+      float x[64];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = col_base + 16 * j + i;
+          v[i] = (rv && col < P.d) ? P.x_in[grow * P.d + col] : 0.0f;
+          x[16 * j + i] = v[i];
+        }
+        store_a_chunk(smem, row, col_base + 16 * j, v, with_lo);
+        signal_chunk(smem, 4 * ch + j, lane);
+      }
+      int until_keep = P.thin_start, kept = P.kept_base;
+      RngStream rs;
+      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = P.rng.ctr_base;
+
+      for (int k = 0; k < P.n_steps; ++k) {
+        const int ti = k & tab.mask;
+        const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
+        // E1: z1 -> h1 (A of GEMM2), act'(z1) -> TMEM
+        mbar_wait(acc_bar, parity); parity ^= 1;
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = col_base + 16 * j;
+          float v[16], s[16];
+          tmem_ld16(lane_addr + 0 + c0, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) act_fast<ACT>(v[i] + b1[c0 + i], v[i], s[i]);
+          tmem_st16(lane_addr + 256 + c0, s);
+          store_a_chunk(smem, row, c0, v, with_lo);
+          tcgen05_fence_before();
+          signal_chunk(smem, 4 * ch + j, lane);
+        }
+        tmem_st_wait();
+        // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
+        mbar_wait(acc_bar, parity); parity ^= 1;
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = col_base + 16 * j;
+          float v[16];
+          tmem_ld16(lane_addr + 128 + c0, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float hh, dh;
+            act_fast<ACT>(v[i] + b2[c0 + i], hh, dh);
+            v[i] = w3[c0 + i] * dh;
+          }
+          store_a_chunk(smem, row, c0, v, with_lo);
+          tcgen05_fence_before();
+          signal_chunk(smem, 4 * ch + j, lane);
+        }
+        // E3: t -> delta1 = t * act'(z1) (A of GEMM4)
+        mbar_wait(acc_bar, parity); parity ^= 1;
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = col_base + 16 * j;
+          float v[16], s[16];
+          tmem_ld16(lane_addr + 0 + c0, v);
+          tmem_ld16(lane_addr + 256 + c0, s);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= s[i];
+          store_a_chunk(smem, row, c0, v, with_lo);
+          tcgen05_fence_before();
+          signal_chunk(smem, 4 * ch + j, lane);
+        }
+        // E4: g -> Langevin update of x; new x = A of the next step's GEMM1
+        mbar_wait(acc_bar, parity); parity ^= 1;
+        tcgen05_fence_after();
+        const bool last = (k == P.n_steps - 1);
+        bool keep_now = false;
+        if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = col_base + 16 * j;
+          float g[16], eps[16];
+          tmem_ld16(lane_addr + 128 + c0, g);
+          const long long li0 = grow * P.d + c0;
+          if (P.rng.mode == 2 && quad_rng) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
+              const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base,
+                                            (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
+              const float4 nn = normal4(w);
+              eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool in = rv && (c0 + i) < P.d;
+              float ev = 0.0f;
+              if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
+              eps[i] = ev;
+            }
+          }
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x1 = __fsub_rn(x[16 * j + i], __fmul_rn(h, g[i]));
+            float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
+            if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
+            xn = (rv && (c0 + i) < P.d) ? xn : 0.0f;
+            x[16 * j + i] = xn;
+            v[i] = xn;
+          }
+          if (keep_now) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (rv && (c0 + i) < P.d) P.traj[(grow * P.n_kept + kept) * P.d + c0 + i] = v[i];
+          }
+          if (!last) {
+            store_a_chunk(smem, row, c0, v, with_lo);
+            tcgen05_fence_before();
+            signal_chunk(smem, 4 * ch + j, lane);
+          }
+        }
+        if (keep_now) ++kept;
+        else if (P.traj && until_keep == P.thin && kept >= P.n_kept) ++kept;
+        rs.ctr_base += P.rng.ctr_step;
+      }
+      if (rv) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (col_base + i < P.d) P.x_out[grow * P.d + col_base + i] = x[i];
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
+  const EbmEnergyDesc* e = c.e;
+  if (e->dim > kTcW || e->hidden1 > kTcW || e->hidden2 > kTcW) {
+    set_error("tensor-core MLP kernel supports widths up to %d", kTcW);
+    return EBM_ERR_UNSUPPORTED;
+  }
+  const DeviceInfo& di = device_info(current_device());
+  const long long numel = (long long)c.n * e->dim;
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  P.W1 = e->buf[0]; P.b1 = e->buf[1]; P.W2 = e->buf[2]; P.b2 = e->buf[3]; P.w3 = e->buf[4];
+  P.d = e->dim; P.h1 = e->hidden1; P.h2 = e->hidden2;
+  P.passes = passes;
+  P.n = c.n;
+  P.thin = c.thin;
+  P.n_kept = c.n_steps / c.thin;
+  P.has_clamp = c.clamp != nullptr;
+  if (c.clamp) { P.clamp_lo = c.clamp[0]; P.clamp_hi = c.clamp[1]; }
+  P.traj = c.traj;
+  P.rng.mode = c.rng_mode;
+  if (c.rng_mode == EBM_RNG_TORCH) {
+    P.rng.T = torch_threads(di, numel);
+    P.rng.k0 = (uint32_t)c.seed; P.rng.k1 = (uint32_t)(c.seed >> 32);
+    P.rng.ctr_step = torch_offset_increment(di, numel) / 4;
+  } else {
+    P.rng.T = 1;
+    P.rng.k0 = (uint32_t)c.seed ^ kNativeTag0; P.rng.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
+    P.rng.ctr_step = 1;
+  }
+  long long tiles = (c.n + kTcM - 1) / kTcM;
+  const int grid = (int)(tiles < di.sm_count ? tiles : di.sm_count);
+  const bool uniform = c.schedule_len == 1;
+  int done = 0;
+  const float* src = c.x_in;
+  while (done < c.n_steps) {
+    const int chunk = uniform ? c.n_steps : ((c.n_steps - done < kSchedChunk) ? (c.n_steps - done) : kSchedChunk);
+    StepTable tab;
+    memset(&tab, 0, sizeof(tab));
+    if (uniform) { fill_step(tab, 0, c.hs[0], c.nss[0]); tab.mask = 0; }
+    else { for (int i = 0; i < chunk; ++i) fill_step(tab, i, c.hs[done + i], c.nss[done + i]); tab.mask = ~0; }
+    P.x_in = src;
+    P.x_out = c.x_out;
+    P.n_steps = chunk;
+    P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
+    P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;
+    P.thin_start = c.thin - (done % c.thin);
+    P.kept_base = done / c.thin;
+#define CALL(A)                                                                                               \
+  {                                                                                                           \
+    auto kern = langevin_mlp_tc_kernel<A>;                                                                    \
+    EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmemLayout::total));   \
+    kern<<<grid, kTcThreads, TcSmemLayout::total, c.st>>>(P, tab);                                            \
+  }
+    switch (e->activation) {
+      case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;
+      case EBM_ACT_TANH: CALL(EBM_ACT_TANH); break;
+      case EBM_ACT_RELU: CALL(EBM_ACT_RELU); break;
+      default: CALL(EBM_ACT_SOFTPLUS); break;
+    }
+#undef CALL
+    int rc = launch_status("langevin_mlp_tc_kernel");
+    if (rc) return rc;
+    done += chunk;
+    src = c.x_out;
+  }
+  return 0;
+}
+
+}  // namespace ebm
