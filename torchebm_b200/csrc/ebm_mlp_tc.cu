@@ -27,7 +27,8 @@ using namespace umma;
 constexpr int kTcM = 128;          // chains per tile = TMEM lanes
 constexpr int kTcW = 128;          // padded width of every layer
 constexpr int kTcChunks = kTcW / 16;
-constexpr int kTcEpiWarps = 8;
+constexpr int kTcEpiWarps = 16;         // 4 lane quarters x 4 column quarters
+constexpr int kTcCols = kTcW / (kTcEpiWarps / 4);  // columns per epilogue thread (32)
 constexpr int kTcThreads = 32 * (1 + kTcEpiWarps);
 constexpr int kTcMatBytes = kTcW * kTcW * 2;  // one bf16 [128 x 128] operand
 
@@ -65,30 +66,35 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// write 16 consecutive columns [col0, col0+16) of row r of the A operand (hi and lo copies)
-__device__ __forceinline__ void store_a_chunk(uint8_t* smem, int r, int col0, const float (&v)[16], bool with_lo) {
+// write kTcCols consecutive columns [col0, col0 + 32) of row r of the A operand (hi and lo copies); 8 columns = one
+// 16-byte core-matrix row, consecutive rows of a warp are consecutive 16-byte slots (conflict-free st.shared.v4)
+__device__ __forceinline__ void store_a_cols(uint8_t* smem, int r, int col0, const float (&v)[kTcCols], bool with_lo) {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  for (int oct = 0; oct < kTcCols / 8; ++oct) {
     uint32_t ph[4], pl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[half * 8 + 2 * j], h0, l0);
-      split_bf16(v[half * 8 + 2 * j + 1], h1, l1);
-      ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      const float a = v[oct * 8 + 2 * j], b = v[oct * 8 + 2 * j + 1];
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+      ph[j] = hu;
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
+      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
     }
-    const int off = core_offset(r, col0 + half * 8, kTcM);
+    const int off = core_offset(r, col0 + oct * 8, kTcM);
     *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     if (with_lo) *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
-// all lanes of the warp have written their rows of one chunk: publish it to the MMA warp
-__device__ __forceinline__ void signal_chunk(uint8_t* smem, int chunk, int lane) {
+// all lanes of the warp have written their rows of the warp's two 16-column chunks: publish them to the MMA warp
+__device__ __forceinline__ void signal_cols(uint8_t* smem, int first_chunk, int lane) {
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) mbar_arrive(smem_u32(smem + TcSmemLayout::bars + chunk * 8));
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < kTcCols / 16; ++c) mbar_arrive(smem_u32(smem + TcSmemLayout::bars + (first_chunk + c) * 8));
+  }
 }
 
 template <int ACT>
@@ -196,13 +202,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
   } else {
     // ---- epilogue warps -------------------------------------------------------------------------
     const int e = warp - 1;
-    const int row = 32 * (warp & 3) + lane;        // TMEM lane this thread may access
-    const int ch = e >> 2;                          // column half
-    const int col_base = 64 * ch;
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    const float* b1 = reinterpret_cast<const float*>(smem + TcSmemLayout::b1);
-    const float* b2 = reinterpret_cast<const float*>(smem + TcSmemLayout::b2);
-    const float* w3 = reinterpret_cast<const float*>(smem + TcSmemLayout::w3);
+    const int row = 32 * (warp & 3) + lane;        // TMEM lane this thread may access (hardware: warp % 4)
+    const int cq = e >> 2;                          // column quarter
+    const int col_base = kTcCols * cq;
+    const int first_chunk = col_base / 16;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + col_base;
+    const float* b1 = reinterpret_cast<const float*>(smem + TcSmemLayout::b1) + col_base;
+    const float* b2 = reinterpret_cast<const float*>(smem + TcSmemLayout::b2) + col_base;
+    const float* w3 = reinterpret_cast<const float*>(smem + TcSmemLayout::w3) + col_base;
     const uint32_t acc_bar = smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8);
     const bool with_lo = P.passes == 3;
     const long long numel = P.n * P.d;
@@ -212,19 +219,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long grow = tile * kTcM + row;
       const bool rv = grow < P.n;
-      float x[64];
+      float x[kTcCols];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = col_base + 16 * j + i;
-          v[i] = (rv && col < P.d) ? P.x_in[grow * P.d + col] : 0.0f;
-          x[16 * j + i] = v[i];
-        }
-        store_a_chunk(smem, row, col_base + 16 * j, v, with_lo);
-        signal_chunk(smem, 4 * ch + j, lane);
+      for (int i = 0; i < kTcCols; ++i) {
+        const int col = col_base + i;
+        x[i] = (rv && col < P.d) ? P.x_in[grow * P.d + col] : 0.0f;
       }
+      store_a_cols(smem, row, col_base, x, with_lo);
+      signal_cols(smem, first_chunk, lane);
       int until_keep = P.thin_start, kept = P.kept_base;
       RngStream rs;
       rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = P.rng.ctr_base;
@@ -232,113 +234,100 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
       for (int k = 0; k < P.n_steps; ++k) {
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
-        // E1: z1 -> h1 (A of GEMM2), act'(z1) -> TMEM
+        float v[kTcCols];
+        // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM columns [256, 384)
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = col_base + 16 * j;
-          float v[16], s[16];
-          tmem_ld16(lane_addr + 0 + c0, v);
+        tmem_ld32_nowait(lane_addr + 0, v);
+        tmem_ld_wait();
+        {
+          float s[kTcCols];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) act_fast<ACT>(v[i] + b1[c0 + i], v[i], s[i]);
-          tmem_st16(lane_addr + 256 + c0, s);
-          store_a_chunk(smem, row, c0, v, with_lo);
-          tcgen05_fence_before();
-          signal_chunk(smem, 4 * ch + j, lane);
+          for (int i = 0; i < kTcCols; ++i) act_fast<ACT>(v[i] + b1[i], v[i], s[i]);
+          tmem_st32(lane_addr + 256, s);
         }
-        tmem_st_wait();
+        store_a_cols(smem, row, col_base, v, with_lo);
+        tcgen05_fence_before();
+        signal_cols(smem, first_chunk, lane);
         // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = col_base + 16 * j;
-          float v[16];
-          tmem_ld16(lane_addr + 128 + c0, v);
+        tmem_ld32_nowait(lane_addr + 128, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float hh, dh;
-            act_fast<ACT>(v[i] + b2[c0 + i], hh, dh);
-            v[i] = w3[c0 + i] * dh;
-          }
-          store_a_chunk(smem, row, c0, v, with_lo);
-          tcgen05_fence_before();
-          signal_chunk(smem, 4 * ch + j, lane);
+        for (int i = 0; i < kTcCols; ++i) {
+          float hh, dh;
+          act_fast<ACT>(v[i] + b2[i], hh, dh);
+          v[i] = w3[i] * dh;
         }
+        store_a_cols(smem, row, col_base, v, with_lo);
+        tcgen05_fence_before();
+        signal_cols(smem, first_chunk, lane);
         // E3: t -> delta1 = t * act'(z1) (A of GEMM4)
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = col_base + 16 * j;
-          float v[16], s[16];
-          tmem_ld16(lane_addr + 0 + c0, v);
-          tmem_ld16(lane_addr + 256 + c0, s);
+        {
+          float s[kTcCols];
+          tmem_st_wait();
+          tmem_ld32_nowait(lane_addr + 0, v);
+          tmem_ld32_nowait(lane_addr + 256, s);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= s[i];
-          store_a_chunk(smem, row, c0, v, with_lo);
-          tcgen05_fence_before();
-          signal_chunk(smem, 4 * ch + j, lane);
+          for (int i = 0; i < kTcCols; ++i) v[i] *= s[i];
         }
-        // E4: g -> Langevin update of x; new x = A of the next step's GEMM1
+        store_a_cols(smem, row, col_base, v, with_lo);
+        tcgen05_fence_before();
+        signal_cols(smem, first_chunk, lane);
+        // E4: g -> Langevin update of x; the new x is the A operand of the next step's GEMM1
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
+        tmem_ld32_nowait(lane_addr + 128, v);
         const bool last = (k == P.n_steps - 1);
         bool keep_now = false;
-        if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; }
+        if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
+        float eps[kTcCols];
+        const long long li0 = grow * P.d + col_base;
+        if (P.rng.mode == 2 && quad_rng) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = col_base + 16 * j;
-          float g[16], eps[16];
-          tmem_ld16(lane_addr + 128 + c0, g);
-          const long long li0 = grow * P.d + c0;
-          if (P.rng.mode == 2 && quad_rng) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
-              const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base,
-                                            (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
-              const float4 nn = normal4(w);
-              eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool in = rv && (c0 + i) < P.d;
-              float ev = 0.0f;
-              if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
-              eps[i] = ev;
-            }
+          for (int q4 = 0; q4 < kTcCols / 4; ++q4) {
+            const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
+            const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base,
+                                          (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
+            const float4 nn = normal4_fast(w);
+            eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
           }
-          float v[16];
+        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x1 = __fsub_rn(x[16 * j + i], __fmul_rn(h, g[i]));
-            float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
-            if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
-            xn = (rv && (c0 + i) < P.d) ? xn : 0.0f;
-            x[16 * j + i] = xn;
-            v[i] = xn;
-          }
-          if (keep_now) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (rv && (c0 + i) < P.d) P.traj[(grow * P.n_kept + kept) * P.d + c0 + i] = v[i];
-          }
-          if (!last) {
-            store_a_chunk(smem, row, c0, v, with_lo);
-            tcgen05_fence_before();
-            signal_chunk(smem, 4 * ch + j, lane);
+          for (int i = 0; i < kTcCols; ++i) {
+            const bool in = rv && (col_base + i) < P.d;
+            float ev = 0.0f;
+            if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
+            eps[i] = ev;
           }
         }
-        if (keep_now) ++kept;
-        else if (P.traj && until_keep == P.thin && kept >= P.n_kept) ++kept;
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < kTcCols; ++i) {
+          const float x1 = __fsub_rn(x[i], __fmul_rn(h, v[i]));
+          float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
+          if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
+          x[i] = (rv && (col_base + i) < P.d) ? xn : 0.0f;
+        }
+        if (keep_now) {
+#pragma unroll
+          for (int i = 0; i < kTcCols; ++i)
+            if (rv && (col_base + i) < P.d) P.traj[(grow * P.n_kept + (kept - 1)) * P.d + col_base + i] = x[i];
+        }
+        if (!last) {
+          store_a_cols(smem, row, col_base, x, with_lo);
+          tcgen05_fence_before();
+          signal_cols(smem, first_chunk, lane);
+        }
         rs.ctr_base += P.rng.ctr_step;
       }
       if (rv) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
+        for (int i = 0; i < kTcCols; ++i)
           if (col_base + i < P.d) P.x_out[grow * P.d + col_base + i] = x[i];
       }
     }
