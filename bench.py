@@ -278,24 +278,39 @@ def run_ours(args):
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc_text, "rng": "torch-layout Philox4x32-10 drawn in-kernel",
+        "config": {"workload": desc_text,
+                   "rng": ("native-layout" if args.workload.startswith("mlp128") else "torch-layout") + " Philox4x32-10 drawn in-kernel",
                    "chains_per_gpu": n_local, "collective": "all_gather of [N/W, D] shards at burst end" if world > 1 else "none",
                    "l2": "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events"},
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind + " (burst copy)",
-                     "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-                     "kernel_ms": kernel_ms / args.steps,
+        "roofline": roofline(args.workload, peaks, peak_kind, achieved, traffic, algo_bytes_per_launch, kernel_ms / args.steps,
+                             n_local * units_per_chain),
+    }
+    line["roofline"].update({
                      "note": "SURVEY 8(d) streaming model: 8*D bytes per chain-step (16*D per HMC leapfrog step); the burst "
                              "keeps the chain in registers, so real DRAM traffic is 8*D*N bytes per BURST and the kernel is "
-                             "instruction-issue bound; see DESIGN.md and profiles/"},
-    }
+                             "instruction-issue bound; see DESIGN.md and profiles/"})
     if args.workload in ("c2", "mlp128") and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=args.cpu_k if args.workload == "c2" else 2)
         line["torch_cuda_baseline"] = torch_cuda_baseline(dev, args.workload)
     print(json.dumps(line))
+
+
+def roofline(workload, peaks, peak_kind, achieved_gbs, traffic, algo_bytes, kernel_ms, units_per_launch):
+    """HBM streaming model for the analytic paths; tensor-pipe model (4*(D*H + H*H + H) FLOP per chain-step,
+    against the measured bf16 burst peak) for the MLP path."""
+    if workload.startswith("mlp128"):
+        flops = 4 * (128 * 128 + 128 * 128 + 128) * units_per_launch
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
+                "algorithmic_flops_per_launch": flops, "kernel_ms": kernel_ms,
+                "hbm_streaming_model_gbs": achieved_gbs}
+    return {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind + " (burst copy)",
+            "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms}
 
 
 def _oracle_energy(workload, device="cpu"):

@@ -164,9 +164,14 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     P.ctr_base = c.offset / 4 + (unsigned long long)done * P.ctr_step;
     P.thin_start = c.thin - (done % c.thin);
     P.kept_base = done / c.thin;
-#define LAUNCH(RNG)                                                                                         \
-  if (c.traj) langevin_elem_kernel<ElemE, RNG, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);        \
-  else        langevin_elem_kernel<ElemE, RNG, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);
+#define LAUNCH(RNG)                                                                                          \
+  if (c.traj) {                                                                                              \
+    if (c.clamp) langevin_elem_kernel<ElemE, RNG, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);   \
+    else         langevin_elem_kernel<ElemE, RNG, true, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);  \
+  } else {                                                                                                   \
+    if (c.clamp) langevin_elem_kernel<ElemE, RNG, false, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);  \
+    else         langevin_elem_kernel<ElemE, RNG, false, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab); \
+  }
     if (c.rng_mode == EBM_RNG_INJECTED) { LAUNCH(0) }
     else if (c.rng_mode == EBM_RNG_TORCH) { LAUNCH(1) }
     else { LAUNCH(2) }

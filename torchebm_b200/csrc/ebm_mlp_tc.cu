@@ -87,6 +87,31 @@ __device__ __forceinline__ void store_a_cols(uint8_t* smem, int r, int col0, con
   }
 }
 
+// 16-column variant (one MMA k-step) used to publish the first half of a thread's columns early
+__device__ __forceinline__ void store_a_16(uint8_t* smem, int r, int col0, const float* v, bool with_lo) {
+#pragma unroll
+  for (int oct = 0; oct < 2; ++oct) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[oct * 8 + 2 * j], b = v[oct * 8 + 2 * j + 1];
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+      ph[j] = hu;
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
+      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const int off = core_offset(r, col0 + oct * 8, kTcM);
+    *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+__device__ __forceinline__ void signal_one(uint8_t* smem, int chunk, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(smem_u32(smem + TcSmemLayout::bars + chunk * 8));
+}
+
 // all lanes of the warp have written their rows of the warp's two 16-column chunks: publish them to the MMA warp
 __device__ __forceinline__ void signal_cols(uint8_t* smem, int first_chunk, int lane) {
   fence_proxy_async();
@@ -145,7 +170,12 @@ __device__ __forceinline__ void tc_issue_gemm(uint8_t* smem, uint32_t tmem_d, in
   const uint32_t a_hi = smem_u32(smem + TcSmemLayout::a_hi), a_lo = smem_u32(smem + TcSmemLayout::a_lo);
   const uint32_t w_hi = smem_u32(smem + w_hi_off), w_lo = smem_u32(smem + w_lo_off);
   const uint32_t idesc = make_idesc_bf16(kTcM, kTcW, backward);
-  for (int c = 0; c < ksteps; ++c) {
+  // every epilogue thread publishes its first 16-column block half-way through its work and the second at the
+  // end, so the even chunks are ready early: consume evens first, then odds (summation order is irrelevant)
+  bool first = true;
+  for (int idx = 0; idx < kTcChunks; ++idx) {
+    const int c = (idx < kTcChunks / 2) ? 2 * idx : 2 * (idx - kTcChunks / 2) + 1;
+    if (c >= ksteps) continue;
     mbar_wait(smem_u32(smem + TcSmemLayout::bars + c * 8), parity);
     tcgen05_fence_after();
     const uint32_t a_off = c * 2 * (kTcM * 16);
@@ -154,7 +184,8 @@ __device__ __forceinline__ void tc_issue_gemm(uint8_t* smem, uint32_t tmem_d, in
     const uint32_t b_lbo = backward ? 128 : kTcW * 16, b_sbo = backward ? kTcW * 16 : 128;
     const uint64_t ah = make_smem_desc(a_hi + a_off, kTcM * 16, 128);
     const uint64_t bh = make_smem_desc(w_hi + b_off, b_lbo, b_sbo);
-    mma_bf16(tmem_d, ah, bh, idesc, c > 0);
+    mma_bf16(tmem_d, ah, bh, idesc, !first);
+    first = false;
     if (passes == 3) {
       const uint64_t al = make_smem_desc(a_lo + a_off, kTcM * 16, 128);
       const uint64_t bl = make_smem_desc(w_lo + b_off, b_lbo, b_sbo);
@@ -234,94 +265,99 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
       for (int k = 0; k < P.n_steps; ++k) {
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
-        float v[kTcCols];
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM columns [256, 384)
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-        tmem_ld32_nowait(lane_addr + 0, v);
-        tmem_ld_wait();
-        {
-          float s[kTcCols];
 #pragma unroll
-          for (int i = 0; i < kTcCols; ++i) act_fast<ACT>(v[i] + b1[i], v[i], s[i]);
-          tmem_st32(lane_addr + 256, s);
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16], s[16];
+          tmem_ld16(lane_addr + 0 + 16 * blk, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) act_fast<ACT>(v[i] + b1[16 * blk + i], v[i], s[i]);
+          tmem_st16(lane_addr + 256 + 16 * blk, s);
+          store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+          tcgen05_fence_before();
+          signal_one(smem, first_chunk + blk, lane);
         }
-        store_a_cols(smem, row, col_base, v, with_lo);
-        tcgen05_fence_before();
-        signal_cols(smem, first_chunk, lane);
         // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-        tmem_ld32_nowait(lane_addr + 128, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < kTcCols; ++i) {
-          float hh, dh;
-          act_fast<ACT>(v[i] + b2[i], hh, dh);
-          v[i] = w3[i] * dh;
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16];
+          tmem_ld16(lane_addr + 128 + 16 * blk, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float hh, dh;
+            act_fast<ACT>(v[i] + b2[16 * blk + i], hh, dh);
+            v[i] = w3[16 * blk + i] * dh;
+          }
+          store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+          tcgen05_fence_before();
+          signal_one(smem, first_chunk + blk, lane);
         }
-        store_a_cols(smem, row, col_base, v, with_lo);
-        tcgen05_fence_before();
-        signal_cols(smem, first_chunk, lane);
         // E3: t -> delta1 = t * act'(z1) (A of GEMM4)
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-        {
-          float s[kTcCols];
-          tmem_st_wait();
-          tmem_ld32_nowait(lane_addr + 0, v);
-          tmem_ld32_nowait(lane_addr + 256, s);
-          tmem_ld_wait();
+        tmem_st_wait();
 #pragma unroll
-          for (int i = 0; i < kTcCols; ++i) v[i] *= s[i];
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16], s[16];
+          tmem_ld16(lane_addr + 0 + 16 * blk, v);
+          tmem_ld16(lane_addr + 256 + 16 * blk, s);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= s[i];
+          store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+          tcgen05_fence_before();
+          signal_one(smem, first_chunk + blk, lane);
         }
-        store_a_cols(smem, row, col_base, v, with_lo);
-        tcgen05_fence_before();
-        signal_cols(smem, first_chunk, lane);
         // E4: g -> Langevin update of x; the new x is the A operand of the next step's GEMM1
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-        tmem_ld32_nowait(lane_addr + 128, v);
         const bool last = (k == P.n_steps - 1);
         bool keep_now = false;
         if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
-        float eps[kTcCols];
-        const long long li0 = grow * P.d + col_base;
-        if (P.rng.mode == 2 && quad_rng) {
 #pragma unroll
-          for (int q4 = 0; q4 < kTcCols / 4; ++q4) {
-            const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
-            const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base,
-                                          (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
-            const float4 nn = normal4_fast(w);
-            eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
+        for (int blk = 0; blk < 2; ++blk) {
+          float g[16], eps[16];
+          const int c0 = col_base + 16 * blk;
+          const long long li0 = grow * P.d + c0;
+          if (P.rng.mode == 2 && quad_rng) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
+              const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base,
+                                            (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
+              const float4 nn = normal4_fast(w);
+              eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool in = rv && (c0 + i) < P.d;
+              float ev = 0.0f;
+              if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
+              eps[i] = ev;
+            }
           }
-        } else {
+          tmem_ld16(lane_addr + 128 + 16 * blk, g);
 #pragma unroll
-          for (int i = 0; i < kTcCols; ++i) {
-            const bool in = rv && (col_base + i) < P.d;
-            float ev = 0.0f;
-            if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
-            eps[i] = ev;
+          for (int i = 0; i < 16; ++i) {
+            const float x1 = __fsub_rn(x[16 * blk + i], __fmul_rn(h, g[i]));
+            float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
+            if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
+            x[16 * blk + i] = (rv && (c0 + i) < P.d) ? xn : 0.0f;
           }
-        }
-        tmem_ld_wait();
+          if (keep_now) {
 #pragma unroll
-        for (int i = 0; i < kTcCols; ++i) {
-          const float x1 = __fsub_rn(x[i], __fmul_rn(h, v[i]));
-          float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
-          if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
-          x[i] = (rv && (col_base + i) < P.d) ? xn : 0.0f;
-        }
-        if (keep_now) {
-#pragma unroll
-          for (int i = 0; i < kTcCols; ++i)
-            if (rv && (col_base + i) < P.d) P.traj[(grow * P.n_kept + (kept - 1)) * P.d + col_base + i] = x[i];
-        }
-        if (!last) {
-          store_a_cols(smem, row, col_base, x, with_lo);
-          tcgen05_fence_before();
-          signal_cols(smem, first_chunk, lane);
+            for (int i = 0; i < 16; ++i)
+              if (rv && (c0 + i) < P.d) P.traj[(grow * P.n_kept + (kept - 1)) * P.d + c0 + i] = x[16 * blk + i];
+          }
+          if (!last) {
+            store_a_16(smem, row, c0, x + 16 * blk, with_lo);
+            tcgen05_fence_before();
+            signal_one(smem, first_chunk + blk, lane);
+          }
         }
         rs.ctr_base += P.rng.ctr_step;
       }

@@ -45,7 +45,7 @@ struct LangevinElemParams {
   unsigned long long n_quads;   // number of owning threads
 };
 
-template <class EnergyT, int RNG, bool TRAJ>
+template <class EnergyT, int RNG, bool TRAJ, bool CLAMP>
 __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constant__ LangevinElemParams P,
                                                             const EnergyT en,
                                                             const __grid_constant__ StepTable tab) {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
       // x1 = x + h*(1.0*(-g)) ; dw = eps*c1 ; x' = x1 + c2*dw   (base_integrator.py:387-397,728-729)
       const float x1 = __fsub_rn(x[i], __fmul_rn(h, g));
       float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(e[i], c1)));
-      if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
+      if (CLAMP) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
       x[i] = xn;
     }
     if (TRAJ) {
