@@ -38,6 +38,8 @@ WORKLOADS = {
     "mlp128_fp32": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (fp32 FFMA kernel)", 65536, 128, 100),
     "mlp128_bf16": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (single-pass bf16)", 65536, 128, 100),
     "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
+    "c3": ("ContrastiveDivergence persistent=True negatives: replay-buffer gather -> LangevinDynamics MLP 784-128-128-1 SiLU "
+           "k=20 step_size=0.01 -> FIFO write-back; n_chains=65536=buffer_size", 65536, 784, 20),
 }
 METRIC = "langevin_chain_steps_per_sec"
 UNIT = "chain-steps/s"
@@ -124,7 +126,8 @@ def dist_setup(n_gpus: int):
 
 
 def make_workload(name: str, n_local: int, dev):
-    """Returns (step_fn(x_in, out, seed_offset) -> launches, desc, algorithmic bytes per chain-step, units per step)."""
+    """Returns (step_fn(x_in, out, it, kev) -> launches, desc, model, algorithmic bytes per chain-step, units per chain).
+    `kev` = (start, end) CUDA events the step records around its dominant kernel (None: do not record)."""
     import torchebm_b200 as te
     from torchebm_b200 import _lib, ops
 
@@ -134,8 +137,10 @@ def make_workload(name: str, n_local: int, dev):
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
 
-        def step(x, out, it):
+        def step(x, out, it, kev=None):
+            if kev: kev[0].record()
             ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            if kev: kev[1].record()
             return 1
 
         return step, desc, model, 8 * d, k
@@ -146,8 +151,10 @@ def make_workload(name: str, n_local: int, dev):
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_NATIVE)
 
-        def step(x, out, it):
+        def step(x, out, it, kev=None):
+            if kev: kev[0].record()
             ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=1234, offset=it * inc, out=out)
+            if kev: kev[1].record()
             return 1
 
         return step, desc, model, 8 * d, k
@@ -156,11 +163,33 @@ def make_workload(name: str, n_local: int, dev):
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_hmc(dev, n_local, d, 1, _lib.RNG_TORCH)
 
-        def step(x, out, it):
+        def step(x, out, it, kev=None):
+            if kev: kev[0].record()
             ops.hmc_burst(desc, x, 1, k, [0.01], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            if kev: kev[1].record()
             return 1
 
         return step, desc, model, 16 * d, k
+    if name == "c3":
+        torch.manual_seed(0)
+        model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev)
+        sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=dev, rng="native")
+        cd = te.ContrastiveDivergence(model, sampler, k_steps=k, persistent=True, buffer_size=n_local, init_steps=0,
+                                      new_sample_ratio=0.0, device=dev)
+        gen = torch.Generator(dev).manual_seed(1234)
+        desc = te.energy_descriptor(model, d, dev)
+
+        def step(x, out, it, kev=None):
+            # the sampling half of ContrastiveDivergence.forward (losses/contrastive_divergence.py:127-139): start points
+            # from the replay buffer, K-step negative chain, FIFO write-back.  The loss/backward is the training objective.
+            start = cd.get_start_points(x, generator=gen)
+            if kev: kev[0].record()
+            neg = sampler.sample(x=start, n_steps=k, generator=gen)
+            if kev: kev[1].record()
+            cd.update_buffer(neg)
+            return 4  # pcd_gather, mlp_wide_prep, langevin_mlp_wide, pcd_scatter
+
+        return step, desc, model, 8 * d, k
     raise KeyError(name)
 
 
@@ -211,9 +240,7 @@ def run_ours(args):
         for it in range(args.steps):
             flush.zero_()  # evict the state from L2 between timed iterations (not timed)
             starts[it].record()
-            kstarts[it].record()
-            launches += step(x_local, out_local, args.warmup + it)
-            kends[it].record()
+            launches += step(x_local, out_local, args.warmup + it, (kstarts[it], kends[it]))
             if world > 1:
                 gather_chains(out_local, out=gathered)
             ends[it].record()
@@ -279,7 +306,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc_text,
-                   "rng": ("native-layout" if args.workload.startswith("mlp128") else "torch-layout") + " Philox4x32-10 drawn in-kernel",
+                   "rng": ("native-layout" if args.workload.startswith("mlp128") or args.workload == "c3" else "torch-layout") + " Philox4x32-10 drawn in-kernel",
                    "chains_per_gpu": n_local, "collective": "all_gather of [N/W, D] shards at burst end" if world > 1 else "none",
                    "l2": "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events"},
         "e2e": e2e,
@@ -292,7 +319,7 @@ def run_ours(args):
                      "note": "SURVEY 8(d) streaming model: 8*D bytes per chain-step (16*D per HMC leapfrog step); the burst "
                              "keeps the chain in registers, so real DRAM traffic is 8*D*N bytes per BURST and the kernel is "
                              "instruction-issue bound; see DESIGN.md and profiles/"})
-    if args.workload in ("c2", "mlp128") and world == 1 and not args.no_cpu_baseline:
+    if args.workload in ("c2", "mlp128", "c3") and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=args.cpu_k if args.workload == "c2" else 2)
         line["torch_cuda_baseline"] = torch_cuda_baseline(dev, args.workload)
     print(json.dumps(line))
@@ -301,8 +328,9 @@ def run_ours(args):
 def roofline(workload, peaks, peak_kind, achieved_gbs, traffic, algo_bytes, kernel_ms, units_per_launch):
     """HBM streaming model for the analytic paths; tensor-pipe model (4*(D*H + H*H + H) FLOP per chain-step,
     against the measured bf16 burst peak) for the MLP path."""
-    if workload.startswith("mlp128"):
-        flops = 4 * (128 * 128 + 128 * 128 + 128) * units_per_launch
+    if workload.startswith("mlp128") or workload == "c3":
+        d_in = 784 if workload == "c3" else 128
+        flops = 4 * (d_in * 128 + 128 * 128 + 128) * units_per_launch
         ach = flops / (kernel_ms * 1e-3) / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
@@ -318,6 +346,8 @@ def _oracle_energy(workload, device="cpu"):
 
     if workload.startswith("mlp128"):
         return E.make_mlp(128, (128, 128), "silu", seed=0).to(device)
+    if workload == "c3":
+        return E.make_mlp(784, (128, 128), "silu", seed=0).to(device)
     return E.DoubleWell(2.0, 1.0)
 
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 2
+#define EBM_ABI_VERSION 3
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -52,7 +52,8 @@ enum { EBM_MASS_NONE = 0, EBM_MASS_SCALAR = 1, EBM_MASS_VECTOR = 2 };
 /* Arithmetic of the MLP-energy products.
  *   FP32  : fp32 FFMA on the CUDA cores (summation order differs from cuBLAS, ~1e-6 relative).
  *   BF16X3: tcgen05 tensor cores, every operand split into bf16 hi + lo, hi*hi + lo*hi + hi*lo accumulated in fp32
- *           tensor memory (~2e-5 relative); the default of the Python samplers.
+ *           tensor memory (~2e-5 relative); the default of the Python samplers.  Widths: D <= 128 keeps the chain
+ *           on chip for the whole burst; 128 < D <= 4096 (e.g. 784-128-128-1) streams the state and W1 per step.
  *   BF16  : tcgen05 tensor cores, single bf16 pass (~4e-3 relative). */
 enum { EBM_MLP_FP32 = 0, EBM_MLP_BF16X3 = 1, EBM_MLP_BF16 = 2 };
 
@@ -74,7 +75,10 @@ typedef struct EbmEnergyDesc {
    *   Gaussian: buf[0] = mean[D], buf[1] = cov_inv[D,D]
    *   MoG     : buf[0] = means[K,D], buf[1] = sigmas[K], buf[2] = weights[K]
    *   MLP     : buf[0] = W1[H1,D], buf[1] = b1[H1], buf[2] = W2[H2,H1], buf[3] = b2[H2],
-   *             buf[4] = w3[H2], buf[5] = b3[1]            (torch [out,in] layout)   */
+   *             buf[4] = w3[H2], buf[5] = b3[1]            (torch [out,in] layout);
+   *             buf[6] = scratch workspace of ebm_mlp_workspace_bytes() bytes, 128-byte aligned, required by the
+   *             Langevin burst when D > 128 (the burst re-splits the weights into it at every call; one workspace
+   *             must not be shared by bursts running concurrently on different streams)   */
   const float* buf[8];
 } EbmEnergyDesc;
 
@@ -86,6 +90,9 @@ const char* ebm_last_error(void);
 int     ebm_device_sm_count(int device);
 int64_t ebm_torch_rng_threads(int device, int64_t numel);
 int64_t ebm_torch_rng_offset_increment(int device, int64_t numel);
+
+/* Bytes of device scratch the Langevin burst needs in e->buf[6] (0 when the energy needs none). */
+int64_t ebm_mlp_workspace_bytes(const EbmEnergyDesc* e);
 
 /* E(x) -> energy[n]; replaces `model(x)` (BaseModel.forward, base_model.py:49-60). */
 int ebm_energy_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, void* stream);

@@ -69,6 +69,7 @@ LANGEVIN_CASES = [
     "langevin_doublewell", "langevin_doublewell_odd", "langevin_doublewell_k100", "langevin_harmonic",
     "langevin_rastrigin", "langevin_gaussian_c1", "langevin_gaussian_d16", "langevin_single_chain",
     "langevin_scheduled", "langevin_mlp_silu", "langevin_mlp_tanh", "langevin_mlp_d128", "langevin_mog",
+    "langevin_mlp_d784",
 ]
 # cases whose closed-form gradient is bit-identical to the reference's autograd on CPU
 LANGEVIN_BITEXACT_CLOSED = {

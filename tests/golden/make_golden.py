@@ -37,7 +37,12 @@ def _import_reference():
     return tmp
 
 
+ONLY = set(sys.argv[1:])  # optional: regenerate only the named cases
+
+
 def save(name, **arrs):
+    if ONLY and name not in ONLY:
+        return
     out = {}
     for k, v in arrs.items():
         if torch.is_tensor(v):
@@ -102,7 +107,7 @@ def main():
         s = LangevinDynamics(model, step_size=h, noise_scale=ns, clamp=kw.pop("clamp", None))
         res = s.sample(x=x0, n_steps=k, generator=torch.Generator().manual_seed(seed), **kw)
         arrs = dict(x0=x0, noise=noise, k=k, h=h if isinstance(h, float) else -1.0, ns=ns if isinstance(ns, float) else -1.0)
-        if noise.numel() > 200_000:
+        if noise.numel() > 100_000:
             # too big to commit: the test re-draws it from the CPU generator seed and checks the checksum
             del arrs["noise"]
             arrs["noise_seed"] = seed
@@ -248,6 +253,17 @@ def main():
         _, neg = cd2(data[it], generator=g)
         negs.append(neg.detach()); bufs.append(cd2.replay_buffer.clone()); ptrs.append(cd2._buffer_ptr_int)
     save("pcd_doublewell_fifo", data=data, seed=5, negs=torch.stack(negs), bufs=torch.stack(bufs), ptrs=np.array(ptrs))
+
+    # wide-state MLP energy (BASELINE configs C3/C5: dim 784): ragged single tile, narrow hidden layers.  Own
+    # manual_seed so that adding it did not shift the parameter draws of the cases above.
+    torch.manual_seed(4321)
+    m = MLPEnergy(784, 64, torch.nn.SiLU)
+    lin = [l for l in m.net if isinstance(l, torch.nn.Linear)]
+    extra = {}
+    for i, l in enumerate(lin):
+        extra[f"w{i}"] = l.weight.detach()
+        extra[f"b{i}"] = l.bias.detach()
+    langevin_case("langevin_mlp_d784", m, 40, 784, 4, 0.01, 1.0, 21, extra=extra)
 
 
 if __name__ == "__main__":

@@ -153,6 +153,7 @@ def _oracle_for(name, g):
     ("langevin_mog", 2000, 6, 10),
     ("langevin_mlp_silu", 1000, 16, 5),
     ("langevin_mlp_d128", 4096, 128, 5),
+    ("langevin_mlp_d784", 300, 784, 3),         # wide-state kernel: 2 full tiles + a ragged one
 ])
 def test_same_seed_matches_reference_stream_on_cuda(name, n, d, k):
     """rng='torch': the sampler consumes torch's CUDA Philox stream exactly like the reference's per-step
@@ -185,7 +186,7 @@ def test_same_seed_matches_reference_stream_on_cuda(name, n, d, k):
 
 
 @pytest.mark.parametrize("precision,rtol,atol", [("fp32", 1e-4, 2e-5), ("bf16x3", 1e-4, 2e-5), ("bf16", 5e-2, 5e-3)])
-@pytest.mark.parametrize("name", ["langevin_mlp_silu", "langevin_mlp_tanh", "langevin_mlp_d128"])
+@pytest.mark.parametrize("name", ["langevin_mlp_silu", "langevin_mlp_tanh", "langevin_mlp_d128", "langevin_mlp_d784"])
 def test_mlp_precisions_match_reference_golden(name, precision, rtol, atol):
     """fp32 = CUDA-core FFMA kernel; bf16x3 / bf16 = tcgen05 tensor-core kernel (split operands / single pass)."""
     import torchebm_b200 as te
@@ -196,7 +197,10 @@ def test_mlp_precisions_match_reference_golden(name, precision, rtol, atol):
     model.precision = precision
     x0 = g["x0"].to(DEV)
     desc = te.energy_descriptor(model, x0.shape[1], x0.device)
-    assert desc.c.precision == _lib.MLP_PRECISIONS[precision]
+    if x0.shape[1] > 128 and precision == "fp32":
+        assert desc.c.precision == _lib.MLP_BF16X3  # wide states run on the tensor cores only (same accuracy class)
+    else:
+        assert desc.c.precision == _lib.MLP_PRECISIONS[precision]
     noise = C.langevin_noise(g).to(DEV)
     out = ops.langevin_burst(desc, x0, int(g["k"]), [float(g["h"])], [float(g["ns"])], rng_mode=_lib.RNG_INJECTED, noise=noise)
     torch.testing.assert_close(out.cpu(), g["out"], rtol=rtol, atol=atol)
@@ -227,6 +231,47 @@ def test_mlp_tensor_core_kernel_many_tiles_trajectory_and_native_rng(precision):
     model.precision = "fp32" if precision == "bf16x3" else "bf16x3"
     c = sn.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(1))
     torch.testing.assert_close(a, c, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("d,hidden,act", [(784, (128, 128), "silu"), (200, (128, 96), "tanh"), (130, (40, 128), "softplus"),
+                                          (320, (64, 64), "relu")])
+def test_wide_mlp_kernel_many_tiles_ragged_dims_trajectory(d, hidden, act):
+    """Streamed-operand kernel (dim > 128): more tiles than SMs, ragged last tile, state widths that are not a
+    multiple of the 64-column chunk / of 16 / of 4, clamp + thinned trajectory, torch and native RNG."""
+    import torchebm_b200 as te
+    from torchebm_b200 import ops
+
+    torch.manual_seed(1)
+    model = te.MLPEnergy(dim=d, hidden=hidden, activation=act).to(DEV)
+    lin = [l for l in model.net if isinstance(l, torch.nn.Linear)]
+    en = E.MLP([l.weight for l in lin], [l.bias for l in lin], act)
+    n = 148 * 128 + 77 if d == 784 else 700
+    x0 = torch.randn(n, d, device=DEV).clamp_(-3, 3)
+    keep = x0.clone()
+    s = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, clamp=(-2.5, 2.5), device=DEV)
+    got = s.sample(x=x0, n_steps=4, thin=2, return_trajectory=True, generator=torch.Generator(DEV).manual_seed(9))
+    want = olang.sample(en, x0, 4, 0.01, 0.5, clamp=(-2.5, 2.5), thin=2, return_trajectory=True,
+                        generator=torch.Generator(DEV).manual_seed(9))
+    assert got.shape == (n, 2, d) and torch.equal(x0, keep)
+    if act == "relu":  # act' jumps at 0: a pre-activation within rounding of the kink may take the other branch
+        bad = ((got - want).abs() > 2e-5 + 1e-4 * want.abs()).float().mean().item()
+        assert bad < 1e-4, bad
+    else:
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
+    # energy / gradient entry points of the same descriptor
+    desc = te.energy_descriptor(model, d, x0.device)
+    torch.testing.assert_close(ops.gradient(desc, x0[:333]), en.gradient(x0[:333]), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(ops.energy(desc, x0[:333]), en.energy(x0[:333]).detach(), rtol=1e-5, atol=1e-4)
+    # native stream: deterministic, finite, and a scheduled (per-step table) burst equals the constant one
+    sn = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, device=DEV, rng="native")
+    a = sn.sample(x=x0, n_steps=3, generator=torch.Generator(DEV).manual_seed(1))
+    b = sn.sample(x=x0, n_steps=3, generator=torch.Generator(DEV).manual_seed(1))
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    # in place (x_out aliases x_in)
+    from torchebm_b200 import _lib
+    x1 = x0.clone()
+    ops.langevin_burst(desc, x1, 3, [0.01], [0.5], rng_mode=_lib.RNG_NATIVE, seed=1, offset=0, out=x1)
+    assert torch.equal(x1, a)
 
 
 def test_x_none_draws_initial_state_from_generator():

@@ -13,7 +13,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libebm_b200.so")
 
-EBM_ABI_VERSION = 2
+EBM_ABI_VERSION = 3
 
 ENERGY_DOUBLE_WELL, ENERGY_HARMONIC, ENERGY_RASTRIGIN, ENERGY_GAUSSIAN, ENERGY_MOG, ENERGY_MLP = range(6)
 ACT_SILU, ACT_TANH, ACT_RELU, ACT_SOFTPLUS = range(4)
@@ -62,6 +62,7 @@ PROTOTYPES = {
     "ebm_device_sm_count": (C.c_int, [C.c_int]),
     "ebm_torch_rng_threads": (_I64, [C.c_int, _I64]),
     "ebm_torch_rng_offset_increment": (_I64, [C.c_int, _I64]),
+    "ebm_mlp_workspace_bytes": (_I64, [_DESC]),
     "ebm_energy_f32": (C.c_int, [_DESC, _P, _I64, _P, _P]),
     "ebm_gradient_f32": (C.c_int, [_DESC, _P, _I64, _P, _P]),
     "ebm_euler_maruyama_step_f32": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _F64, _P]),

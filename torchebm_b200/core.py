@@ -19,6 +19,7 @@ attributes in `energy_descriptor`).
 
 from __future__ import annotations
 
+import ctypes as C
 import math
 import warnings
 from abc import ABC, abstractmethod
@@ -403,7 +404,23 @@ def _match_mlp(net) -> Optional[Tuple[nn.Linear, nn.Linear, nn.Linear, int]]:
 # --------------------------------------------------------------------------------------------------
 # descriptor extraction
 
-MLP_MAX_WIDTH = 128  # kMlpMax of csrc/ebm_mlp.cu
+MLP_MAX_WIDTH = 128  # kMlpMax of csrc/ebm_mlp.cu: hidden widths, and the state width of the on-chip kernels
+MLP_MAX_DIM = 4096   # kWdMaxDim of csrc/ebm_mlp_wide.cu: state width of the streamed-operand kernel
+
+_WORKSPACES: dict = {}
+
+
+def _mlp_workspace(device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) scratch for the wide-MLP burst: descriptors are rebuilt at every `sample()` call, the
+    workspace is not.  Bursts on one stream are ordered, so sharing it among them is safe."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
 
 
 class EnergyDescriptor:
@@ -479,14 +496,22 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         l1, l2, l3, act = m
         if l1.in_features != dim:
             return None
-        if max(l1.in_features, l1.out_features, l2.out_features) > MLP_MAX_WIDTH:
-            return None  # no fused kernel yet: integrator-level path (own autograd + fused update)
+        if max(l1.out_features, l2.out_features) > MLP_MAX_WIDTH or l1.in_features > MLP_MAX_DIM:
+            return None  # no fused kernel: integrator-level path (own autograd + fused update)
         ts = [_dev_f32(t, device) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight.reshape(-1), l3.bias)]
         d.kind = _lib.ENERGY_MLP
         d.hidden1, d.hidden2, d.activation = l1.out_features, l2.out_features, act
-        d.precision = _lib.MLP_PRECISIONS[getattr(model, "precision", "bf16x3")]
+        precision = getattr(model, "precision", "bf16x3")
+        if l1.in_features > MLP_MAX_WIDTH and precision == "fp32":
+            precision = "bf16x3"  # wide states have a tensor-core kernel only (same accuracy class as fp32)
+        d.precision = _lib.MLP_PRECISIONS[precision]
         for i, t in enumerate(ts):
             d.buf[i] = t.data_ptr()
+        ws_bytes = int(_lib.load().ebm_mlp_workspace_bytes(C.byref(d)))
+        if ws_bytes > 0:  # wide states: scratch for the per-burst bf16 hi/lo re-split of the weights
+            ws = _mlp_workspace(device, ws_bytes)
+            d.buf[6] = ws.data_ptr()
+            ts.append(ws)
         return EnergyDescriptor(d, ts, "mlp")
     return None
 

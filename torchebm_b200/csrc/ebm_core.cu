@@ -259,6 +259,7 @@ static int langevin_dispatch(const LangevinCall& c) {
 
 int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                              cudaStream_t st);  // ebm_mlp.cu
+size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e);  // ebm_mlp_wide.cu
 
 }  // namespace ebm
 
@@ -288,6 +289,11 @@ int ebm_rng_fill_f32(float* out, int64_t numel, int32_t rng_mode, int32_t kind, 
   else { s.T = 1; s.k0 = (uint32_t)seed ^ kNativeTag0; s.k1 = (uint32_t)(seed >> 32) ^ kNativeTag1; }
   rng_fill_kernel<<<flat_grid(di, numel, 256), 256, 0, (cudaStream_t)stream>>>(out, numel, s, kind);
   return launch_status("rng_fill_kernel");
+}
+
+int64_t ebm_mlp_workspace_bytes(const EbmEnergyDesc* e) {
+  if (!e || e->kind != EBM_ENERGY_MLP || e->dim <= 128) return 0;
+  return (int64_t)mlp_wide_workspace_bytes(e);
 }
 
 int ebm_energy_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, void* stream) {

@@ -384,8 +384,12 @@ static int mlp_grid(const DeviceInfo& di, long long n) {
     default: CALL(EBM_ACT_SOFTPLUS); break;                \
   }
 
+int mlp_wide_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
+                                  cudaStream_t st);  // ebm_mlp_wide.cu
+
 int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                              cudaStream_t st) {
+  if (e->dim > kMlpMax) return mlp_wide_energy_grad_dispatch(e, x, n, energy, grad, st);
   MlpParams P;
   int rc = fill_mlp(e, P);
   if (rc) return rc;
@@ -402,9 +406,16 @@ int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, 
   return launch_status("mlp_energy_grad_kernel");
 }
 
-int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes);  // ebm_mlp_tc.cu
+int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes);    // ebm_mlp_tc.cu
+int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes);  // ebm_mlp_wide.cu
 
 int langevin_mlp_dispatch(const LangevinCall& c) {
+  if (c.e->dim > kMlpMax) {  // state wider than one tile: streamed-operand tensor-core kernel
+    if (c.e->precision == EBM_MLP_BF16X3) return langevin_mlp_wide_dispatch(c, 3);
+    if (c.e->precision == EBM_MLP_BF16) return langevin_mlp_wide_dispatch(c, 1);
+    set_error("MLP energies with dim > %d run on the tensor-core kernel only (precision bf16x3 or bf16)", kMlpMax);
+    return EBM_ERR_UNSUPPORTED;
+  }
   if (c.e->precision == EBM_MLP_BF16X3) return langevin_mlp_tc_dispatch(c, 3);
   if (c.e->precision == EBM_MLP_BF16) return langevin_mlp_tc_dispatch(c, 1);
   if (c.e->precision != EBM_MLP_FP32) { set_error("bad MLP precision %d", c.e->precision); return EBM_ERR_INVALID; }

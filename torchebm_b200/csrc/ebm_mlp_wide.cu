@@ -1,0 +1,831 @@
+// MLP-energy Langevin burst for WIDE inputs (dim > 128, hidden widths <= 128) on tcgen05 + TMEM, sm_100a only:
+// the 784-128-128-1 energies of BASELINE configs C3 / C5 (persistent CD on image-sized states).
+//
+// Same math as ebm_mlp_tc.cu (bf16 hi+lo split operands, three passes per product, fp32 accumulators in tensor
+// memory), but neither the chain state (128 x 784 fp32 = 392 KB per tile) nor W1 (784 x 128, 392 KB as bf16 hi+lo)
+// fits on chip, so both stream:
+//   * W1 (pre-split by mlp_wide_prep_kernel into 64-column chunks, each chunk one contiguous 32 KB blob already in the
+//     tensor-core core-matrix layout) and W2 (hi blob, lo blob) travel through a 4-stage shared-memory ring filled by
+//     cp.async.bulk (the TMA bulk engine) with mbarrier complete_tx; the ring item order per step is fixed:
+//         W2hi, W2lo, W1[0], W1[1], ..., W1[NC-1]
+//   * x streams through global memory (L2 resident between steps: 148 tiles x 392 KB < L2): every step each element
+//     is read once and written once -- the 8*D bytes per chain-step of the streaming roofline model.
+// The trick that keeps W1 traffic at ONE pass per step: the input-gradient product G = delta1 . W1 is produced in
+// 64-column chunks, and chunk c of W1 (MN-major view) serves G_c of step k and then, untouched in the same ring stage
+// (K-major view), the forward product z1 += x'_c . W1_c^T of step k+1 as soon as the epilogue has turned G_c into the
+// updated state chunk x'_c.  Per step and tile:
+//     [E1 -> GEMM2 -> E2 -> GEMM3 -> E3]   then for c in chunks: GEMM4_c -> E4_c (update, RNG, store x) -> GEMM1'_c
+// Warp roles: warp 0 = TMEM allocation + single-thread MMA issue, warp 1 = bulk-copy producer, warps 2..17 = epilogue
+// (thread = one chain row x 32 hidden columns in the 128-wide phases, x 16 state columns per chunk in the E4 phase).
+// TMEM columns: [0,128) z1 / t, [128,256) z2, [256,384) act'(z1), [384,448) G even chunks, [448,512) G odd chunks.
+#include "api_common.cuh"
+#include "umma.cuh"
+#include <cuda_bf16.h>
+
+namespace ebm {
+
+using namespace umma;
+
+constexpr int kWdM = 128;               // chains per tile = TMEM lanes
+constexpr int kWdH = 128;               // padded hidden width
+constexpr int kWdChunk = 64;            // state columns per W1 ring item
+constexpr int kWdStageBytes = 32768;    // ring item: W1 chunk hi (16 KB) + lo (16 KB), or W2 hi, or W2 lo
+constexpr int kWdHalf = 16384;
+constexpr int kWdStages = 4;
+constexpr int kWdEpiWarps = 16;
+constexpr int kWdThreads = 32 * (2 + kWdEpiWarps);
+constexpr int kWdMaxDim = 4096;
+
+struct WdSmem {
+  static constexpr int ring = 0;
+  static constexpr int a_hi = ring + kWdStages * kWdStageBytes;  // [128 x 128] bf16: h1 / delta2 / delta1
+  static constexpr int a_lo = a_hi + kWdM * kWdH * 2;
+  static constexpr int xa_hi = a_lo + kWdM * kWdH * 2;           // [128 x 64] bf16: state chunk (A of GEMM1)
+  static constexpr int xa_lo = xa_hi + kWdM * kWdChunk * 2;
+  static constexpr int b1 = xa_lo + kWdM * kWdChunk * 2;
+  static constexpr int b2 = b1 + kWdH * 4;
+  static constexpr int w3 = b2 + kWdH * 4;
+  static constexpr int bars = w3 + kWdH * 4;
+  // barrier indices (8 bytes each)
+  static constexpr int ring_full = 0;                 // [kWdStages], tx-count
+  static constexpr int ring_empty = ring_full + kWdStages;   // [kWdStages], tcgen05.commit
+  static constexpr int xa_full = ring_empty + kWdStages;     // 16 epilogue warps
+  static constexpr int xa_empty = xa_full + 1;        // tcgen05.commit
+  static constexpr int g_full = xa_empty + 1;         // [2], tcgen05.commit
+  static constexpr int a_chunk = g_full + 2;          // [8], 4 warps each
+  static constexpr int acc_full = a_chunk + 8;        // tcgen05.commit
+  static constexpr int n_bars = acc_full + 1;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+static_assert(WdSmem::total <= 232448, "shared memory budget of one sm_100 CTA exceeded");
+
+struct WdParams {
+  const uint8_t* ws;  // workspace: NC W1 chunk blobs, W2 hi blob, W2 lo blob (mlp_wide_prep_kernel)
+  const float* b1; const float* b2; const float* w3;
+  int d, h1, h2, nc;
+  int passes;
+  const float* x_in;
+  float* x_out;
+  const float* noise;
+  float* traj;
+  long long n;
+  int n_steps, thin, n_kept, thin_start, kept_base, has_clamp;
+  float clamp_lo, clamp_hi;
+  RowRng rng;
+};
+
+__device__ __forceinline__ uint32_t wd_bar(uint8_t* smem, int idx) { return smem_u32(smem + WdSmem::bars + idx * 8); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// global -> shared bulk copy on the TMA engine; completion is signalled as `bytes` transaction bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---- weight preparation ---------------------------------------------------------------------------------
+// One thread = one 16-byte core-matrix row (8 consecutive k of one output row) of the hi and of the lo copy.
+__global__ void mlp_wide_prep_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int d, int h1, int h2,
+                                     int nc, uint8_t* __restrict__ ws) {
+  const int per_chunk = kWdH * (kWdChunk / 8);
+  const int n_w1 = nc * per_chunk;
+  const int n_w2 = kWdH * (kWdH / 8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_w1 + n_w2; i += gridDim.x * blockDim.x) {
+    float v[8];
+    uint8_t* hi_dst;
+    uint8_t* lo_dst;
+    if (i < n_w1) {
+      const int c = i / per_chunk, rem = i - c * per_chunk;
+      const int oct = rem / kWdH, r = rem - oct * kWdH;  // consecutive threads -> consecutive rows -> consecutive 16 B
+      const int col0 = c * kWdChunk + oct * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (r < h1 && col0 + j < d) ? W1[(long long)r * d + col0 + j] : 0.0f;
+      hi_dst = ws + (size_t)c * kWdStageBytes + core_offset(r, oct * 8, kWdH);
+      lo_dst = hi_dst + kWdHalf;
+    } else {
+      const int rem = i - n_w1;
+      const int oct = rem / kWdH, r = rem - oct * kWdH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (r < h2 && oct * 8 + j < h1) ? W2[r * h1 + oct * 8 + j] : 0.0f;
+      hi_dst = ws + (size_t)nc * kWdStageBytes + core_offset(r, oct * 8, kWdH);
+      lo_dst = hi_dst + kWdStageBytes;
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h2v = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2v);
+      ph[j] = hu;
+      const __nv_bfloat162 l2v =
+          __floats2bfloat162_rn(v[2 * j] - __uint_as_float(hu << 16), v[2 * j + 1] - __uint_as_float(hu & 0xffff0000u));
+      pl[j] = *reinterpret_cast<const uint32_t*>(&l2v);
+    }
+    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(lo_dst) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// ---- epilogue helpers -----------------------------------------------------------------------------------
+// 16 consecutive columns [col0, col0+16) of row r -> hi and lo copies of a [128 x C] core-matrix operand
+__device__ __forceinline__ void wd_store16(uint8_t* hi_base, uint8_t* lo_base, int r, int col0, const float* v, bool with_lo) {
+#pragma unroll
+  for (int oct = 0; oct < 2; ++oct) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[oct * 8 + 2 * j], b = v[oct * 8 + 2 * j + 1];
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+      ph[j] = hu;
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
+      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const int off = core_offset(r, col0 + oct * 8, kWdM);
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// make this warp's generic-proxy shared-memory writes visible to the tensor core, then one arrival per warp
+__device__ __forceinline__ void wd_publish(uint32_t bar, int lane) {
+  tcgen05_fence_before();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+template <int ACT>
+__device__ __forceinline__ void wd_act(float z, float& h, float& dh) {
+  if (ACT == EBM_ACT_SILU) {
+    const float s = __frcp_rn(1.0f + __expf(-z));
+    h = z * s;
+    dh = s * (1.0f + z * (1.0f - s));
+  } else if (ACT == EBM_ACT_TANH) {
+    const float e = __expf(-2.0f * fabsf(z));
+    const float t = copysignf((1.0f - e) * __frcp_rn(1.0f + e), z);
+    h = t;
+    dh = 1.0f - t * t;
+  } else if (ACT == EBM_ACT_RELU) {
+    h = z > 0.0f ? z : 0.0f;
+    dh = z > 0.0f ? 1.0f : 0.0f;
+  } else {
+    h = z > 20.0f ? z : log1pf(__expf(z));
+    dh = __frcp_rn(1.0f + __expf(-z));
+  }
+}
+
+// 16 state columns of one row from global memory (zeros outside the row / the tile)
+__device__ __forceinline__ void wd_load_x16(const float* __restrict__ src, long long grow, int col0, int d, bool rv, bool vec,
+                                            float (&v)[16]) {
+  if (rv && vec && col0 + 16 <= d) {
+    const float4* p = reinterpret_cast<const float4*>(src + grow * d + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = p[j];
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (rv && col0 + j < d) ? src[grow * d + col0 + j] : 0.0f;
+  }
+}
+__device__ __forceinline__ void wd_store_x16(float* __restrict__ dst, long long row_off, int col0, int d, bool rv, bool vec,
+                                             const float (&v)[16]) {
+  if (!rv) return;
+  if (vec && col0 + 16 <= d) {
+    float4* p = reinterpret_cast<float4*>(dst + row_off + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < d) dst[row_off + col0 + j] = v[j];
+  }
+}
+
+// ---- MMA issue helpers (one thread) -----------------------------------------------------------------------
+// `ksteps` k-steps of 16; descriptors advance by (a_step, b_step) bytes per k-step; three passes for split operands
+__device__ __forceinline__ void wd_mma_block(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b_hi,
+                                             uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
+                                             int k_begin, int k_end, int passes, bool accumulate_first) {
+  for (int kk = k_begin; kk < k_end; ++kk) {
+    const uint64_t ah = make_smem_desc(a_hi + kk * a_step, kWdM * 16, 128);
+    const uint64_t bh = make_smem_desc(b_hi + kk * b_step, b_lbo, b_sbo);
+    mma_bf16(tmem_d, ah, bh, idesc, accumulate_first || kk > k_begin);
+    if (passes == 3) {
+      const uint64_t al = make_smem_desc(a_lo + kk * a_step, kWdM * 16, 128);
+      const uint64_t bl = make_smem_desc(b_lo + kk * b_step, b_lbo, b_sbo);
+      mma_bf16(tmem_d, al, bh, idesc, true);
+      mma_bf16(tmem_d, ah, bl, idesc, true);
+    }
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const __grid_constant__ WdParams P,
+                                                                          const __grid_constant__ StepTable tab) {
+  extern __shared__ __align__(128) uint8_t wd_smem_raw[];
+  uint8_t* smem = wd_smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {
+    float* b1 = reinterpret_cast<float*>(smem + WdSmem::b1);
+    float* b2 = reinterpret_cast<float*>(smem + WdSmem::b2);
+    float* w3 = reinterpret_cast<float*>(smem + WdSmem::w3);
+    for (int i = threadIdx.x; i < kWdH; i += blockDim.x) {
+      b1[i] = i < P.h1 ? P.b1[i] : 0.0f;
+      b2[i] = i < P.h2 ? P.b2[i] : 0.0f;
+      w3[i] = i < P.h2 ? P.w3[i] : 0.0f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWdStages; ++s) {
+      mbar_init(wd_bar(smem, WdSmem::ring_full + s), 1);
+      mbar_init(wd_bar(smem, WdSmem::ring_empty + s), 1);
+    }
+    mbar_init(wd_bar(smem, WdSmem::xa_full), kWdEpiWarps);
+    mbar_init(wd_bar(smem, WdSmem::xa_empty), 1);
+    mbar_init(wd_bar(smem, WdSmem::g_full + 0), 1);
+    mbar_init(wd_bar(smem, WdSmem::g_full + 1), 1);
+    for (int c = 0; c < 8; ++c) mbar_init(wd_bar(smem, WdSmem::a_chunk + c), 4);
+    mbar_init(wd_bar(smem, WdSmem::acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(smem + WdSmem::tmem_slot), 512);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + WdSmem::tmem_slot);
+  const long long n_tiles = (P.n + kWdM - 1) / kWdM;
+  const int NC = P.nc;
+  const int K = P.n_steps;
+  const int k_h1 = (P.h1 + 15) / 16, k_h2 = (P.h2 + 15) / 16;
+
+  if (warp == 1) {
+    // ---- producer: stream the weight blobs through the ring in the fixed item order --------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint8_t* w2hi = P.ws + (size_t)NC * kWdStageBytes;
+      const uint8_t* w2lo = w2hi + kWdStageBytes;
+      auto push = [&](const uint8_t* src) {
+        const int s = it % kWdStages;
+        mbar_wait(wd_bar(smem, WdSmem::ring_empty + s), ((it / kWdStages) & 1) ^ 1);
+        const uint32_t full = wd_bar(smem, WdSmem::ring_full + s);
+        mbar_expect_tx(full, kWdStageBytes);
+        bulk_g2s(smem_u32(smem + WdSmem::ring + s * kWdStageBytes), src, kWdStageBytes, full);
+        ++it;
+      };
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < NC; ++c) push(P.ws + (size_t)c * kWdStageBytes);
+        for (int k = 0; k < K; ++k) {
+          push(w2hi);
+          push(w2lo);
+          for (int c = 0; c < NC; ++c) push(P.ws + (size_t)c * kWdStageBytes);
+        }
+      }
+    }
+  } else if (warp == 0) {
+    // ---- MMA issue ----------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t a_hi = smem_u32(smem + WdSmem::a_hi), a_lo = smem_u32(smem + WdSmem::a_lo);
+      const uint32_t xa_hi = smem_u32(smem + WdSmem::xa_hi), xa_lo = smem_u32(smem + WdSmem::xa_lo);
+      const uint32_t ring = smem_u32(smem + WdSmem::ring);
+      const uint32_t idesc_fwd = make_idesc_bf16(kWdM, kWdH, false);
+      const uint32_t idesc_bwd = make_idesc_bf16(kWdM, kWdH, true);
+      const uint32_t core_col = kWdM * 16;  // bytes between 8-column core blocks (R = 128 rows)
+      uint32_t it = 0;                        // ring item counter (consumer side)
+      uint32_t xf_par = 0, a_par = 0;
+      auto ring_wait = [&](uint32_t item) { mbar_wait(wd_bar(smem, WdSmem::ring_full + item % kWdStages), (item / kWdStages) & 1); };
+      auto ring_release = [&](uint32_t item) { mma_commit(wd_bar(smem, WdSmem::ring_empty + item % kWdStages)); };
+      auto stage_addr = [&](uint32_t item) { return ring + (item % kWdStages) * kWdStageBytes; };
+      // forward product of state chunk c: z1 (+)= xa . W1_c^T
+      auto gemm1_chunk = [&](uint32_t item, int c) {
+        const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
+        const uint32_t w = stage_addr(item);
+        wd_mma_block(tmem + 0, xa_hi, xa_lo, 2 * core_col, w, w + kWdHalf, 2 * core_col, core_col, 128, idesc_fwd, 0,
+                     (valid + 15) / 16, P.passes, c > 0);
+      };
+      // input-gradient chunk c: G[c & 1] = delta1 . W1[:, chunk c]   (B = MN-major view of the same bytes)
+      auto gemm4_chunk = [&](uint32_t item, int c) {
+        const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
+        const int ncols = ((valid + 15) / 16) * 16;
+        const uint32_t w = stage_addr(item);
+        wd_mma_block(tmem + 384 + 64 * (c & 1), a_hi, a_lo, 2 * core_col, w, w + kWdHalf, 256, 128, core_col,
+                     make_idesc_bf16(kWdM, ncols, true), 0, k_h1, P.passes, false);
+        mma_commit(wd_bar(smem, WdSmem::g_full + (c & 1)));
+      };
+      // a 128-wide product whose A chunks are published one 16-column chunk at a time by the epilogue
+      auto gemm_chunked = [&](uint32_t tmem_d, uint32_t w_hi, uint32_t w_lo, bool backward, int ksteps) {
+        for (int kk = 0; kk < ksteps; ++kk) {
+          mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
+          tcgen05_fence_after();
+          if (backward)
+            wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 256, 128, core_col, idesc_bwd, kk, kk + 1, P.passes, kk > 0);
+          else
+            wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 2 * core_col, core_col, 128, idesc_fwd, kk, kk + 1,
+                         P.passes, kk > 0);
+        }
+        // chunks beyond ksteps are still published by the epilogue: consume their phases
+        for (int kk = ksteps; kk < 8; ++kk) mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
+        a_par ^= 1;
+      };
+
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < NC; ++c) {  // prologue: z1 of the initial state
+          ring_wait(it);
+          mbar_wait(wd_bar(smem, WdSmem::xa_full), xf_par); xf_par ^= 1;
+          tcgen05_fence_after();
+          gemm1_chunk(it, c);
+          mma_commit(wd_bar(smem, WdSmem::xa_empty));
+          ring_release(it);
+          ++it;
+        }
+        mma_commit(wd_bar(smem, WdSmem::acc_full));
+        for (int k = 0; k < K; ++k) {
+          const bool last = (k == K - 1);
+          ring_wait(it);
+          ring_wait(it + 1);
+          const uint32_t w2hi = stage_addr(it), w2lo = stage_addr(it + 1);
+          gemm_chunked(tmem + 128, w2hi, w2lo, false, k_h1);   // z2 = h1 . W2^T
+          mma_commit(wd_bar(smem, WdSmem::acc_full));
+          gemm_chunked(tmem + 0, w2hi, w2lo, true, k_h2);      // t = delta2 . W2
+          mma_commit(wd_bar(smem, WdSmem::acc_full));
+          ring_release(it);
+          ring_release(it + 1);
+          it += 2;
+          // delta1 fully published -> chunked input gradient + forward product of the next step
+          for (int kk = 0; kk < 8; ++kk) mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
+          a_par ^= 1;
+          tcgen05_fence_after();
+          ring_wait(it);
+          gemm4_chunk(it, 0);
+          if (NC > 1) { ring_wait(it + 1); gemm4_chunk(it + 1, 1); }
+          for (int c = 0; c < NC; ++c) {
+            mbar_wait(wd_bar(smem, WdSmem::xa_full), xf_par); xf_par ^= 1;   // x'_c published, G[c & 1] drained
+            tcgen05_fence_after();
+            if (!last) gemm1_chunk(it + c, c);
+            mma_commit(wd_bar(smem, WdSmem::xa_empty));
+            ring_release(it + c);
+            if (c + 2 < NC) { ring_wait(it + c + 2); gemm4_chunk(it + c + 2, c + 2); }
+          }
+          it += NC;
+          if (!last) mma_commit(wd_bar(smem, WdSmem::acc_full));
+        }
+      }
+      // the last commits must have landed in shared memory before the CTA may retire
+      if (it > 0) mbar_wait(wd_bar(smem, WdSmem::ring_empty + (it - 1) % kWdStages), ((it - 1) / kWdStages) & 1);
+    }
+  } else {
+    // ---- epilogue warps -------------------------------------------------------------------------------------------
+    const int e = warp - 2;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access (hardware: warp % 4)
+    const int cg = e >> 2;                          // column group 0..3
+    const int row = 32 * q + lane;
+    const int hcol = 32 * cg;                       // hidden columns [hcol, hcol + 32) in the 128-wide phases
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    const float* b1 = reinterpret_cast<const float*>(smem + WdSmem::b1) + hcol;
+    const float* b2 = reinterpret_cast<const float*>(smem + WdSmem::b2) + hcol;
+    const float* w3 = reinterpret_cast<const float*>(smem + WdSmem::w3) + hcol;
+    uint8_t* const a_hi = smem + WdSmem::a_hi;
+    uint8_t* const a_lo = smem + WdSmem::a_lo;
+    uint8_t* const xa_hi = smem + WdSmem::xa_hi;
+    uint8_t* const xa_lo = smem + WdSmem::xa_lo;
+    const uint32_t acc_bar = wd_bar(smem, WdSmem::acc_full);
+    const uint32_t xa_full = wd_bar(smem, WdSmem::xa_full), xa_empty = wd_bar(smem, WdSmem::xa_empty);
+    const bool with_lo = P.passes == 3;
+    const bool vec = (P.d % 4 == 0);
+    const long long numel = P.n * P.d;
+    uint32_t acc_par = 0, xe_par = 1, g_par = 0;  // g_par: bit b = parity of g_full[b]
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long grow = tile * kWdM + row;
+      const bool rv = grow < P.n;
+      // prologue: publish the initial state chunk by chunk
+      for (int c = 0; c < NC; ++c) {
+        const int col0 = c * kWdChunk + 16 * cg;
+        float v[16];
+        wd_load_x16(P.x_in, grow, col0, P.d, rv, vec, v);
+        mbar_wait(xa_empty, xe_par); xe_par ^= 1;
+        if (col0 < P.d) wd_store16(xa_hi, xa_lo, row, 16 * cg, v, with_lo);
+        wd_publish(xa_full, lane);
+      }
+      int until_keep = P.thin_start, kept = P.kept_base;
+      RngStream rs;
+      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = P.rng.ctr_base;
+
+      for (int k = 0; k < K; ++k) {
+        const int ti = k & tab.mask;
+        const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
+        const float* xsrc = (k == 0) ? P.x_in : P.x_out;
+        // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM [256, 384)
+        mbar_wait(acc_bar, acc_par); acc_par ^= 1;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16], s[16];
+          tmem_ld16(lane_addr + 0 + hcol + 16 * blk, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wd_act<ACT>(v[i] + b1[16 * blk + i], v[i], s[i]);
+          tmem_st16(lane_addr + 256 + hcol + 16 * blk, s);
+          wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk), lane);
+        }
+        // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
+        mbar_wait(acc_bar, acc_par); acc_par ^= 1;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16];
+          tmem_ld16(lane_addr + 128 + hcol + 16 * blk, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float hh, dh;
+            wd_act<ACT>(v[i] + b2[16 * blk + i], hh, dh);
+            v[i] = w3[16 * blk + i] * dh;
+          }
+          wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk), lane);
+        }
+        // E3: t -> delta1 = t * act'(z1) (A of every GEMM4 chunk)
+        mbar_wait(acc_bar, acc_par); acc_par ^= 1;
+        tcgen05_fence_after();
+        tmem_st_wait();
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16], s[16];
+          tmem_ld16(lane_addr + 0 + hcol + 16 * blk, v);
+          tmem_ld16(lane_addr + 256 + hcol + 16 * blk, s);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= s[i];
+          wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk), lane);
+        }
+        // E4: per 64-column chunk: G_c -> Langevin update of the state chunk -> global + A operand of GEMM1'_c
+        bool keep_now = false;
+        if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
+        float xc[16];
+        wd_load_x16(xsrc, grow, 16 * cg, P.d, rv, vec, xc);
+        for (int c = 0; c < NC; ++c) {
+          const int col0 = c * kWdChunk + 16 * cg;
+          const bool active = col0 < P.d;            // warp-uniform
+          float xnext[16];
+          if (c + 1 < NC) wd_load_x16(xsrc, grow, col0 + kWdChunk, P.d, rv, vec, xnext);
+          float eps[16];
+          if (active) {
+            const long long li0 = grow * P.d + col0;
+            if (rs.mode == 2 && vec && col0 + 16 <= P.d) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint64_t qi = (uint64_t)(li0 + 4 * q4) >> 2;
+                const uint4 w = philox4x32_10((uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)rs.ctr_base,
+                                              (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
+                const float4 nn = normal4_fast(w);
+                eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool in = rv && (col0 + i) < P.d;
+                float ev = 0.0f;
+                if (in) ev = (rs.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
+                eps[i] = ev;
+              }
+            }
+          }
+          mbar_wait(wd_bar(smem, WdSmem::g_full + (c & 1)), (g_par >> (c & 1)) & 1);
+          g_par ^= 1u << (c & 1);
+          tcgen05_fence_after();
+          if (active) {
+            float g[16];
+            tmem_ld16(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x1 = __fsub_rn(xc[i], __fmul_rn(h, g[i]));
+              float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
+              if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
+              xc[i] = (rv && (col0 + i) < P.d) ? xn : 0.0f;
+            }
+            wd_store_x16(P.x_out, grow * P.d, col0, P.d, rv, vec, xc);
+            if (keep_now) wd_store_x16(P.traj, (grow * P.n_kept + (kept - 1)) * P.d, col0, P.d, rv, vec, xc);
+          }
+          mbar_wait(xa_empty, xe_par); xe_par ^= 1;
+          if (active) wd_store16(xa_hi, xa_lo, row, 16 * cg, xc, with_lo);
+          wd_publish(xa_full, lane);
+          if (c + 1 < NC) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xc[i] = xnext[i];
+          }
+        }
+        rs.ctr_base += P.rng.ctr_step;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---- E(x) and grad E(x) for wide MLP energies (diagnostics / ebm_energy_f32 / ebm_gradient_f32) --------------------
+// Plain fp32 FFMA utility kernel, not on the burst path: one warp owns kWdURows rows at a time, the rows are staged in
+// shared memory, lane l owns hidden units l, l+32, l+64, l+96 in the forward products and state columns l + 32 m in the
+// input-gradient product (coalesced W1 reads).  exact expf/tanhf activations as in ebm_mlp.cu.
+constexpr int kWdURows = 4;
+constexpr int kWdUWarps = 4;
+
+template <int ACT>
+__device__ __forceinline__ void wd_act_exact(float z, float& h, float& dh) {
+  if (ACT == EBM_ACT_SILU) {
+    const float s = 1.0f / (1.0f + expf(-z));
+    h = z * s;
+    dh = s * (1.0f + z * (1.0f - s));
+  } else if (ACT == EBM_ACT_TANH) {
+    const float t = tanhf(z);
+    h = t;
+    dh = 1.0f - t * t;
+  } else if (ACT == EBM_ACT_RELU) {
+    h = z > 0.0f ? z : 0.0f;
+    dh = z > 0.0f ? 1.0f : 0.0f;
+  } else {
+    h = z > 20.0f ? z : log1pf(expf(z));
+    dh = 1.0f / (1.0f + expf(-z));
+  }
+}
+
+struct WdUtilParams {
+  const float* W1; const float* b1; const float* W2; const float* b2; const float* w3; const float* b3;
+  int d, h1, h2, dpad;
+  const float* x;
+  float* energy;
+  float* grad;
+  long long n;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(32 * kWdUWarps) mlp_wide_energy_grad_kernel(const WdUtilParams P) {
+  extern __shared__ __align__(16) float wdu_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xs = wdu_smem + (size_t)warp * (kWdURows * (P.dpad + 2 * kWdH));
+  float* hs = xs + kWdURows * P.dpad;
+  float* ds = hs + kWdURows * kWdH;
+  const long long groups = (P.n + kWdURows - 1) / kWdURows;
+  for (long long grp = (long long)blockIdx.x * kWdUWarps + warp; grp < groups; grp += (long long)gridDim.x * kWdUWarps) {
+    const long long row0 = grp * kWdURows;
+    for (int r = 0; r < kWdURows; ++r)
+      for (int k = lane; k < P.dpad; k += 32)
+        xs[r * P.dpad + k] = (row0 + r < P.n && k < P.d) ? P.x[(row0 + r) * P.d + k] : 0.0f;
+    __syncwarp();
+    float acc[kWdURows][4], dh1[kWdURows][4];
+    // layer 1
+#pragma unroll
+    for (int r = 0; r < kWdURows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+    for (int k = 0; k < P.d; ++k) {
+      float w[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { const int j = lane + 32 * v; w[v] = j < P.h1 ? P.W1[(long long)j * P.d + k] : 0.0f; }
+#pragma unroll
+      for (int r = 0; r < kWdURows; ++r) {
+        const float a = xs[r * P.dpad + k];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[r][v] = fmaf(a, w[v], acc[r][v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = lane + 32 * v;
+      const float b = j < P.h1 ? P.b1[j] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < kWdURows; ++r) {
+        float h, dh;
+        wd_act_exact<ACT>(acc[r][v] + b, h, dh);
+        hs[r * kWdH + j] = j < P.h1 ? h : 0.0f;
+        dh1[r][v] = j < P.h1 ? dh : 0.0f;
+      }
+    }
+    __syncwarp();
+    // layer 2 + energy
+#pragma unroll
+    for (int r = 0; r < kWdURows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+    for (int i = 0; i < P.h1; ++i) {
+      float w[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { const int j = lane + 32 * v; w[v] = j < P.h2 ? P.W2[j * P.h1 + i] : 0.0f; }
+#pragma unroll
+      for (int r = 0; r < kWdURows; ++r) {
+        const float a = hs[r * kWdH + i];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[r][v] = fmaf(a, w[v], acc[r][v]);
+      }
+    }
+    float en[kWdURows];
+#pragma unroll
+    for (int r = 0; r < kWdURows; ++r) en[r] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = lane + 32 * v;
+      const float b = j < P.h2 ? P.b2[j] : 0.0f, w3 = j < P.h2 ? P.w3[j] : 0.0f;
+#pragma unroll
+      for (int r = 0; r < kWdURows; ++r) {
+        float h, dh;
+        wd_act_exact<ACT>(acc[r][v] + b, h, dh);
+        en[r] = fmaf(w3, h, en[r]);
+        ds[r * kWdH + j] = w3 * dh;
+      }
+    }
+    if (P.energy) {
+#pragma unroll
+      for (int r = 0; r < kWdURows; ++r) {
+        float e = en[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (lane == 0 && row0 + r < P.n) P.energy[row0 + r] = e + P.b3[0];
+      }
+    }
+    if (P.grad) {
+      __syncwarp();
+      // t = W2^T delta2 ; delta1 = t * act'(z1)
+#pragma unroll
+      for (int r = 0; r < kWdURows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+      for (int j = 0; j < P.h2; ++j) {
+        float w[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { const int i = lane + 32 * v; w[v] = i < P.h1 ? P.W2[j * P.h1 + i] : 0.0f; }
+#pragma unroll
+        for (int r = 0; r < kWdURows; ++r) {
+          const float a = ds[r * kWdH + j];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[r][v] = fmaf(a, w[v], acc[r][v]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int r = 0; r < kWdURows; ++r) hs[r * kWdH + lane + 32 * v] = acc[r][v] * dh1[r][v];
+      __syncwarp();
+      // g = W1^T delta1, 128 state columns per pass
+      for (int kb = 0; kb < P.d; kb += 128) {
+#pragma unroll
+        for (int r = 0; r < kWdURows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+        for (int j = 0; j < P.h1; ++j) {
+          float w[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) { const int k = kb + lane + 32 * v; w[v] = k < P.d ? P.W1[(long long)j * P.d + k] : 0.0f; }
+#pragma unroll
+          for (int r = 0; r < kWdURows; ++r) {
+            const float a = hs[r * kWdH + j];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[r][v] = fmaf(a, w[v], acc[r][v]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int k = kb + lane + 32 * v;
+#pragma unroll
+          for (int r = 0; r < kWdURows; ++r)
+            if (k < P.d && row0 + r < P.n) P.grad[(row0 + r) * P.d + k] = acc[r][v];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+bool mlp_wide_supported(const EbmEnergyDesc* e);
+
+int mlp_wide_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
+                                  cudaStream_t st) {
+  if (!mlp_wide_supported(e)) {
+    set_error("MLP energy %d->%d->%d->1 is not supported (dim <= %d, hidden <= %d)", e->dim, e->hidden1, e->hidden2,
+              kWdMaxDim, kWdH);
+    return EBM_ERR_UNSUPPORTED;
+  }
+  const DeviceInfo& di = device_info(current_device());
+  WdUtilParams P;
+  P.W1 = e->buf[0]; P.b1 = e->buf[1]; P.W2 = e->buf[2]; P.b2 = e->buf[3]; P.w3 = e->buf[4]; P.b3 = e->buf[5];
+  P.d = e->dim; P.h1 = e->hidden1; P.h2 = e->hidden2;
+  P.dpad = (e->dim + 3) & ~3;
+  P.x = x; P.energy = energy; P.grad = grad; P.n = n;
+  const size_t smem = (size_t)kWdUWarps * kWdURows * (P.dpad + 2 * kWdH) * sizeof(float);
+  long long groups = (n + kWdURows - 1) / kWdURows;
+  long long ctas = (groups + kWdUWarps - 1) / kWdUWarps;
+  const long long cap = (long long)di.sm_count * 2;
+  const int grid = (int)(ctas < cap ? ctas : cap);
+#define CALL(A)                                                                                          \
+  {                                                                                                      \
+    auto kern = mlp_wide_energy_grad_kernel<A>;                                                          \
+    EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    kern<<<grid, 32 * kWdUWarps, smem, st>>>(P);                                                         \
+  }
+  switch (e->activation) {
+    case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;
+    case EBM_ACT_TANH: CALL(EBM_ACT_TANH); break;
+    case EBM_ACT_RELU: CALL(EBM_ACT_RELU); break;
+    default: CALL(EBM_ACT_SOFTPLUS); break;
+  }
+#undef CALL
+  return launch_status("mlp_wide_energy_grad_kernel");
+}
+
+size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e) {
+  const int nc = (e->dim + kWdChunk - 1) / kWdChunk;
+  return (size_t)(nc + 2) * kWdStageBytes;
+}
+
+bool mlp_wide_supported(const EbmEnergyDesc* e) {
+  return e->dim <= kWdMaxDim && e->hidden1 <= kWdH && e->hidden2 <= kWdH;
+}
+
+int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
+  const EbmEnergyDesc* e = c.e;
+  if (!mlp_wide_supported(e)) {
+    set_error("wide MLP kernel supports dim <= %d and hidden widths <= %d (got %d-%d-%d)", kWdMaxDim, kWdH, e->dim,
+              e->hidden1, e->hidden2);
+    return EBM_ERR_UNSUPPORTED;
+  }
+  if (!e->buf[6]) {
+    set_error("MLP energies with dim > 128 need a device workspace of ebm_mlp_workspace_bytes() bytes in buf[6]");
+    return EBM_ERR_INVALID;
+  }
+  if (((uintptr_t)e->buf[6] & 127) != 0) { set_error("MLP workspace must be 128-byte aligned"); return EBM_ERR_INVALID; }
+  const DeviceInfo& di = device_info(current_device());
+  const long long numel = (long long)c.n * e->dim;
+  WdParams P;
+  memset(&P, 0, sizeof(P));
+  P.ws = reinterpret_cast<const uint8_t*>(e->buf[6]);
+  P.b1 = e->buf[1]; P.b2 = e->buf[3]; P.w3 = e->buf[4];
+  P.d = e->dim; P.h1 = e->hidden1; P.h2 = e->hidden2;
+  P.nc = (e->dim + kWdChunk - 1) / kWdChunk;
+  P.passes = passes;
+  P.n = c.n;
+  P.thin = c.thin;
+  P.n_kept = c.n_steps / c.thin;
+  P.has_clamp = c.clamp != nullptr;
+  if (c.clamp) { P.clamp_lo = c.clamp[0]; P.clamp_hi = c.clamp[1]; }
+  P.traj = c.traj;
+  P.rng.mode = c.rng_mode;
+  if (c.rng_mode == EBM_RNG_TORCH) {
+    P.rng.T = torch_threads(di, numel);
+    P.rng.k0 = (uint32_t)c.seed; P.rng.k1 = (uint32_t)(c.seed >> 32);
+    P.rng.ctr_step = torch_offset_increment(di, numel) / 4;
+  } else {
+    P.rng.T = 1;
+    P.rng.k0 = (uint32_t)c.seed ^ kNativeTag0; P.rng.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
+    P.rng.ctr_step = 1;
+  }
+  // the weights may have changed since the last burst (training loop): re-split them on the caller's stream
+  {
+    const int items = (P.nc * kWdH * (kWdChunk / 8)) + kWdH * (kWdH / 8);
+    mlp_wide_prep_kernel<<<(items + 255) / 256, 256, 0, c.st>>>(e->buf[0], e->buf[2], P.d, P.h1, P.h2, P.nc,
+                                                                 reinterpret_cast<uint8_t*>(const_cast<float*>(e->buf[6])));
+    int rc = launch_status("mlp_wide_prep_kernel");
+    if (rc) return rc;
+  }
+  long long tiles = (c.n + kWdM - 1) / kWdM;
+  const int grid = (int)(tiles < di.sm_count ? tiles : di.sm_count);
+  const bool uniform = c.schedule_len == 1;
+  int done = 0;
+  const float* src = c.x_in;
+  while (done < c.n_steps) {
+    const int chunk = uniform ? c.n_steps : ((c.n_steps - done < kSchedChunk) ? (c.n_steps - done) : kSchedChunk);
+    StepTable tab;
+    memset(&tab, 0, sizeof(tab));
+    if (uniform) { fill_step(tab, 0, c.hs[0], c.nss[0]); tab.mask = 0; }
+    else { for (int i = 0; i < chunk; ++i) fill_step(tab, i, c.hs[done + i], c.nss[done + i]); tab.mask = ~0; }
+    P.x_in = src;
+    P.x_out = c.x_out;
+    P.n_steps = chunk;
+    P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
+    P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;
+    P.thin_start = c.thin - (done % c.thin);
+    P.kept_base = done / c.thin;
+#define CALL(A)                                                                                            \
+  {                                                                                                        \
+    auto kern = langevin_mlp_wide_kernel<A>;                                                               \
+    EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WdSmem::total));      \
+    kern<<<grid, kWdThreads, WdSmem::total, c.st>>>(P, tab);                                               \
+  }
+    switch (e->activation) {
+      case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;
+      case EBM_ACT_TANH: CALL(EBM_ACT_TANH); break;
+      case EBM_ACT_RELU: CALL(EBM_ACT_RELU); break;
+      default: CALL(EBM_ACT_SOFTPLUS); break;
+    }
+#undef CALL
+    int rc = launch_status("langevin_mlp_wide_kernel");
+    if (rc) return rc;
+    done += chunk;
+    src = c.x_out;
+  }
+  return 0;
+}
+
+}  // namespace ebm
