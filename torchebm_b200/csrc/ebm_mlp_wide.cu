@@ -179,10 +179,28 @@ __device__ __forceinline__ void wd_act(float z, float& h, float& dh) {
   }
 }
 
-// 16 state columns of one row from global memory (zeros outside the row / the tile)
-__device__ __forceinline__ void wd_load_x16(const float* __restrict__ src, long long grow, int col0, int d, bool rv, bool vec,
+// 256-bit global accesses (sm_100): one request per 32-byte sector, so a thread streaming its 64 contiguous bytes of a
+// row never leaves half-used sectors behind for the (tiny, shared-memory-carved) L1 to hold on to
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// 16 state columns of one row from global memory (zeros outside the row / the tile).
+// vec: 2 = rows are 32-byte aligned (d % 8 == 0), 1 = 16-byte aligned (d % 4 == 0), 0 = scalar
+__device__ __forceinline__ void wd_load_x16(const float* __restrict__ src, long long grow, int col0, int d, bool rv, int vec,
                                             float (&v)[16]) {
-  if (rv && vec && col0 + 16 <= d) {
+  if (rv && vec == 2 && col0 + 16 <= d) {
+    const float* p = src + grow * d + col0;
+    ldg256(p, v);
+    ldg256(p + 8, v + 8);
+  } else if (rv && vec == 1 && col0 + 16 <= d) {
     const float4* p = reinterpret_cast<const float4*>(src + grow * d + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -194,10 +212,14 @@ __device__ __forceinline__ void wd_load_x16(const float* __restrict__ src, long 
     for (int j = 0; j < 16; ++j) v[j] = (rv && col0 + j < d) ? src[grow * d + col0 + j] : 0.0f;
   }
 }
-__device__ __forceinline__ void wd_store_x16(float* __restrict__ dst, long long row_off, int col0, int d, bool rv, bool vec,
+__device__ __forceinline__ void wd_store_x16(float* __restrict__ dst, long long row_off, int col0, int d, bool rv, int vec,
                                              const float (&v)[16]) {
   if (!rv) return;
-  if (vec && col0 + 16 <= d) {
+  if (vec == 2 && col0 + 16 <= d) {
+    float* p = dst + row_off + col0;
+    stg256(p, v);
+    stg256(p + 8, v + 8);
+  } else if (vec == 1 && col0 + 16 <= d) {
     float4* p = reinterpret_cast<float4*>(dst + row_off + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -399,7 +421,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     const uint32_t acc_bar = wd_bar(smem, WdSmem::acc_full);
     const uint32_t xa_full = wd_bar(smem, WdSmem::xa_full), xa_empty = wd_bar(smem, WdSmem::xa_empty);
     const bool with_lo = P.passes == 3;
-    const bool vec = (P.d % 4 == 0);
+    // widest aligned access every pointer of this launch allows
+    const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj;
+    const int vec = (P.d % 8 == 0 && (ptr_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (ptr_bits & 15) == 0) ? 1 : 0);
     const long long numel = P.n * P.d;
     uint32_t acc_par = 0, xe_par = 1, g_par = 0;  // g_par: bit b = parity of g_full[b]
 
@@ -469,17 +493,17 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         // E4: per 64-column chunk: G_c -> Langevin update of the state chunk -> global + A operand of GEMM1'_c
         bool keep_now = false;
         if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
-        float xc[16];
-        wd_load_x16(xsrc, grow, 16 * cg, P.d, rv, vec, xc);
         for (int c = 0; c < NC; ++c) {
           const int col0 = c * kWdChunk + 16 * cg;
           const bool active = col0 < P.d;            // warp-uniform
-          float xnext[16];
-          if (c + 1 < NC) wd_load_x16(xsrc, grow, col0 + kWdChunk, P.d, rv, vec, xnext);
+          // the state chunk is requested first (an L2 hit from the previous step's store); the noise draw below
+          // covers its latency
+          float xc[16];
+          if (active) wd_load_x16(xsrc, grow, col0, P.d, rv, vec, xc);
           float eps[16];
           if (active) {
             const long long li0 = grow * P.d + col0;
-            if (rs.mode == 2 && vec && col0 + 16 <= P.d) {
+            if (rs.mode == 2 && P.d % 4 == 0 && col0 + 16 <= P.d) {
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4) {
                 const uint64_t qi = (uint64_t)(li0 + 4 * q4) >> 2;
@@ -517,10 +541,6 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           mbar_wait(xa_empty, xe_par); xe_par ^= 1;
           if (active) wd_store16(xa_hi, xa_lo, row, 16 * cg, xc, with_lo);
           wd_publish(xa_full, lane);
-          if (c + 1 < NC) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xc[i] = xnext[i];
-          }
         }
         rs.ctr_base += P.rng.ctr_step;
       }
