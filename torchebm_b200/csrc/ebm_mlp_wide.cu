@@ -5,7 +5,7 @@
 // memory), but neither the chain state (128 x 784 fp32 = 392 KB per tile) nor W1 (784 x 128, 392 KB as bf16 hi+lo)
 // fits on chip, so both stream:
 //   * W1 (pre-split by mlp_wide_prep_kernel into 64-column chunks, each chunk one contiguous 32 KB blob already in the
-//     tensor-core core-matrix layout) and W2 (hi blob, lo blob) travel through a 4-stage shared-memory ring filled by
+//     tensor-core core-matrix layout) and W2 (hi blob, lo blob) travel through a 3-stage shared-memory ring filled by
 //     cp.async.bulk (the TMA bulk engine) with mbarrier complete_tx; the ring item order per step is fixed:
 //         W2hi, W2lo, W1[0], W1[1], ..., W1[NC-1]
 //   * x streams through global memory (L2 resident between steps: 148 tiles x 392 KB < L2): every step each element
@@ -31,7 +31,7 @@ constexpr int kWdH = 128;               // padded hidden width
 constexpr int kWdChunk = 64;            // state columns per W1 ring item
 constexpr int kWdStageBytes = 32768;    // ring item: W1 chunk hi (16 KB) + lo (16 KB), or W2 hi, or W2 lo
 constexpr int kWdHalf = 16384;
-constexpr int kWdStages = 4;
+constexpr int kWdStages = 3;
 constexpr int kWdEpiWarps = 16;
 constexpr int kWdThreads = 32 * (2 + kWdEpiWarps);
 constexpr int kWdMaxDim = 4096;
@@ -40,18 +40,18 @@ struct WdSmem {
   static constexpr int ring = 0;
   static constexpr int a_hi = ring + kWdStages * kWdStageBytes;  // [128 x 128] bf16: h1 / delta2 / delta1
   static constexpr int a_lo = a_hi + kWdM * kWdH * 2;
-  static constexpr int xa_hi = a_lo + kWdM * kWdH * 2;           // [128 x 64] bf16: state chunk (A of GEMM1)
-  static constexpr int xa_lo = xa_hi + kWdM * kWdChunk * 2;
-  static constexpr int b1 = xa_lo + kWdM * kWdChunk * 2;
+  static constexpr int xa = a_lo + kWdM * kWdH * 2;              // 2 buffers x ([128 x 64] bf16 hi, lo): state chunk, A of GEMM1
+  static constexpr int xa_buf = 2 * kWdM * kWdChunk * 2;         // bytes per buffer (hi then lo)
+  static constexpr int b1 = xa + 2 * xa_buf;
   static constexpr int b2 = b1 + kWdH * 4;
   static constexpr int w3 = b2 + kWdH * 4;
   static constexpr int bars = w3 + kWdH * 4;
   // barrier indices (8 bytes each)
   static constexpr int ring_full = 0;                 // [kWdStages], tx-count
   static constexpr int ring_empty = ring_full + kWdStages;   // [kWdStages], tcgen05.commit
-  static constexpr int xa_full = ring_empty + kWdStages;     // 16 epilogue warps
-  static constexpr int xa_empty = xa_full + 1;        // tcgen05.commit
-  static constexpr int g_full = xa_empty + 1;         // [2], tcgen05.commit
+  static constexpr int xa_full = ring_empty + kWdStages;     // [2], 16 epilogue warps
+  static constexpr int xa_empty = xa_full + 2;        // [2], tcgen05.commit
+  static constexpr int g_full = xa_empty + 2;         // [2], tcgen05.commit
   static constexpr int a_chunk = g_full + 2;          // [8], 4 warps each
   static constexpr int acc_full = a_chunk + 8;        // tcgen05.commit
   static constexpr int n_bars = acc_full + 1;
@@ -152,11 +152,15 @@ __device__ __forceinline__ void wd_store16(uint8_t* hi_base, uint8_t* lo_base, i
 }
 
 // make this warp's generic-proxy shared-memory writes visible to the tensor core, then one arrival per warp
-__device__ __forceinline__ void wd_publish(uint32_t bar, int lane) {
+__device__ __forceinline__ void wd_publish(uint32_t bar) {
   tcgen05_fence_before();
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 st;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
 }
 
 template <int ACT>
@@ -270,8 +274,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       mbar_init(wd_bar(smem, WdSmem::ring_full + s), 1);
       mbar_init(wd_bar(smem, WdSmem::ring_empty + s), 1);
     }
-    mbar_init(wd_bar(smem, WdSmem::xa_full), kWdEpiWarps);
-    mbar_init(wd_bar(smem, WdSmem::xa_empty), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(wd_bar(smem, WdSmem::xa_full + b), kWdEpiWarps);
+      mbar_init(wd_bar(smem, WdSmem::xa_empty + b), 1);
+    }
     mbar_init(wd_bar(smem, WdSmem::g_full + 0), 1);
     mbar_init(wd_bar(smem, WdSmem::g_full + 1), 1);
     for (int c = 0; c < 8; ++c) mbar_init(wd_bar(smem, WdSmem::a_chunk + c), 4);
@@ -316,13 +322,13 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     // ---- MMA issue ----------------------------------------------------------------------------------------------
     if (lane == 0) {
       const uint32_t a_hi = smem_u32(smem + WdSmem::a_hi), a_lo = smem_u32(smem + WdSmem::a_lo);
-      const uint32_t xa_hi = smem_u32(smem + WdSmem::xa_hi), xa_lo = smem_u32(smem + WdSmem::xa_lo);
+      const uint32_t xa = smem_u32(smem + WdSmem::xa);
       const uint32_t ring = smem_u32(smem + WdSmem::ring);
       const uint32_t idesc_fwd = make_idesc_bf16(kWdM, kWdH, false);
       const uint32_t idesc_bwd = make_idesc_bf16(kWdM, kWdH, true);
       const uint32_t core_col = kWdM * 16;  // bytes between 8-column core blocks (R = 128 rows)
       uint32_t it = 0;                        // ring item counter (consumer side)
-      uint32_t xf_par = 0, a_par = 0;
+      uint32_t xcnt = 0, a_par = 0;         // xcnt: running count of published state chunks (buffer = xcnt & 1)
       auto ring_wait = [&](uint32_t item) { mbar_wait(wd_bar(smem, WdSmem::ring_full + item % kWdStages), (item / kWdStages) & 1); };
       auto ring_release = [&](uint32_t item) { mma_commit(wd_bar(smem, WdSmem::ring_empty + item % kWdStages)); };
       auto stage_addr = [&](uint32_t item) { return ring + (item % kWdStages) * kWdStageBytes; };
@@ -330,9 +336,15 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       auto gemm1_chunk = [&](uint32_t item, int c) {
         const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
         const uint32_t w = stage_addr(item);
-        wd_mma_block(tmem + 0, xa_hi, xa_lo, 2 * core_col, w, w + kWdHalf, 2 * core_col, core_col, 128, idesc_fwd, 0,
-                     (valid + 15) / 16, P.passes, c > 0);
+        const uint32_t xa_hi = xa + (xcnt & 1) * WdSmem::xa_buf;
+        wd_mma_block(tmem + 0, xa_hi, xa_hi + WdSmem::xa_buf / 2, 2 * core_col, w, w + kWdHalf, 2 * core_col, core_col, 128,
+                     idesc_fwd, 0, (valid + 15) / 16, P.passes, c > 0);
       };
+      auto xa_wait = [&]() {
+        mbar_wait(wd_bar(smem, WdSmem::xa_full + (xcnt & 1)), (xcnt >> 1) & 1);
+        tcgen05_fence_after();
+      };
+      auto xa_release = [&]() { mma_commit(wd_bar(smem, WdSmem::xa_empty + (xcnt & 1))); ++xcnt; };
       // input-gradient chunk c: G[c & 1] = delta1 . W1[:, chunk c]   (B = MN-major view of the same bytes)
       auto gemm4_chunk = [&](uint32_t item, int c) {
         const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
@@ -361,10 +373,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int c = 0; c < NC; ++c) {  // prologue: z1 of the initial state
           ring_wait(it);
-          mbar_wait(wd_bar(smem, WdSmem::xa_full), xf_par); xf_par ^= 1;
-          tcgen05_fence_after();
+          xa_wait();
           gemm1_chunk(it, c);
-          mma_commit(wd_bar(smem, WdSmem::xa_empty));
+          xa_release();
           ring_release(it);
           ++it;
         }
@@ -389,10 +400,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           gemm4_chunk(it, 0);
           if (NC > 1) { ring_wait(it + 1); gemm4_chunk(it + 1, 1); }
           for (int c = 0; c < NC; ++c) {
-            mbar_wait(wd_bar(smem, WdSmem::xa_full), xf_par); xf_par ^= 1;   // x'_c published, G[c & 1] drained
-            tcgen05_fence_after();
+            xa_wait();                                                       // x'_c published, G[c & 1] drained
             if (!last) gemm1_chunk(it + c, c);
-            mma_commit(wd_bar(smem, WdSmem::xa_empty));
+            xa_release();
             ring_release(it + c);
             if (c + 2 < NC) { ring_wait(it + c + 2); gemm4_chunk(it + c + 2, c + 2); }
           }
@@ -416,16 +426,16 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     const float* w3 = reinterpret_cast<const float*>(smem + WdSmem::w3) + hcol;
     uint8_t* const a_hi = smem + WdSmem::a_hi;
     uint8_t* const a_lo = smem + WdSmem::a_lo;
-    uint8_t* const xa_hi = smem + WdSmem::xa_hi;
-    uint8_t* const xa_lo = smem + WdSmem::xa_lo;
+    uint8_t* const xa = smem + WdSmem::xa;
     const uint32_t acc_bar = wd_bar(smem, WdSmem::acc_full);
     const uint32_t xa_full = wd_bar(smem, WdSmem::xa_full), xa_empty = wd_bar(smem, WdSmem::xa_empty);
+    uint32_t xcnt = 0;  // running count of published state chunks: buffer xcnt & 1, use (xcnt >> 1) of that buffer
     const bool with_lo = P.passes == 3;
     // widest aligned access every pointer of this launch allows
     const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj;
     const int vec = (P.d % 8 == 0 && (ptr_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (ptr_bits & 15) == 0) ? 1 : 0);
     const long long numel = P.n * P.d;
-    uint32_t acc_par = 0, xe_par = 1, g_par = 0;  // g_par: bit b = parity of g_full[b]
+    uint32_t acc_par = 0, g_par = 0;  // g_par: bit b = parity of g_full[b]
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long grow = tile * kWdM + row;
@@ -435,9 +445,12 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const int col0 = c * kWdChunk + 16 * cg;
         float v[16];
         wd_load_x16(P.x_in, grow, col0, P.d, rv, vec, v);
-        mbar_wait(xa_empty, xe_par); xe_par ^= 1;
-        if (col0 < P.d) wd_store16(xa_hi, xa_lo, row, 16 * cg, v, with_lo);
-        wd_publish(xa_full, lane);
+        const uint32_t xb = xcnt & 1;
+        mbar_wait(xa_empty + 8 * xb, ((xcnt >> 1) & 1) ^ 1);
+        ++xcnt;
+        uint8_t* const xa_hi = xa + xb * WdSmem::xa_buf;
+        if (col0 < P.d) wd_store16(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, v, with_lo);
+        wd_publish(xa_full + 8 * xb);
       }
       int until_keep = P.thin_start, kept = P.kept_base;
       RngStream rs;
@@ -458,7 +471,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           for (int i = 0; i < 16; ++i) wd_act<ACT>(v[i] + b1[16 * blk + i], v[i], s[i]);
           tmem_st16(lane_addr + 256 + hcol + 16 * blk, s);
           wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
-          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk), lane);
+          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
@@ -474,7 +487,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
             v[i] = w3[16 * blk + i] * dh;
           }
           wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
-          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk), lane);
+          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E3: t -> delta1 = t * act'(z1) (A of every GEMM4 chunk)
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= s[i];
           wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
-          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk), lane);
+          wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E4: per 64-column chunk: G_c -> Langevin update of the state chunk -> global + A operand of GEMM1'_c
         bool keep_now = false;
@@ -528,19 +541,38 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           if (active) {
             float g[16];
             tmem_ld16(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
+            if (P.has_clamp) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x1 = __fsub_rn(xc[i], __fmul_rn(h, g[i]));
-              float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
-              if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
-              xc[i] = (rv && (col0 + i) < P.d) ? xn : 0.0f;
+              for (int i = 0; i < 16; ++i) {
+                const float x1 = __fsub_rn(xc[i], __fmul_rn(h, g[i]));
+                xc[i] = clamp_torch(__fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1))), P.clamp_lo, P.clamp_hi);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float x1 = __fsub_rn(xc[i], __fmul_rn(h, g[i]));
+                xc[i] = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
+              }
             }
+            if (col0 + 16 > P.d) {  // ragged last block: columns beyond the state stay exactly zero
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xc[i] = (col0 + i) < P.d ? xc[i] : 0.0f;
+            }
+          }
+          // publish the new chunk to the tensor core first (GEMM1' of the next step is on the critical path), then
+          // let the global stores drain underneath the next chunk's noise draw
+          const uint32_t xb = xcnt & 1;
+          mbar_wait(xa_empty + 8 * xb, ((xcnt >> 1) & 1) ^ 1);
+          ++xcnt;
+          if (active) {
+            uint8_t* const xa_hi = xa + xb * WdSmem::xa_buf;
+            wd_store16(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, xc, with_lo);
+          }
+          wd_publish(xa_full + 8 * xb);
+          if (active) {
             wd_store_x16(P.x_out, grow * P.d, col0, P.d, rv, vec, xc);
             if (keep_now) wd_store_x16(P.traj, (grow * P.n_kept + (kept - 1)) * P.d, col0, P.d, rv, vec, xc);
           }
-          mbar_wait(xa_empty, xe_par); xe_par ^= 1;
-          if (active) wd_store16(xa_hi, xa_lo, row, 16 * cg, xc, with_lo);
-          wd_publish(xa_full, lane);
         }
         rs.ctr_base += P.rng.ctr_step;
       }
