@@ -76,9 +76,11 @@ typedef struct EbmEnergyDesc {
    *   MoG     : buf[0] = means[K,D], buf[1] = sigmas[K], buf[2] = weights[K]
    *   MLP     : buf[0] = W1[H1,D], buf[1] = b1[H1], buf[2] = W2[H2,H1], buf[3] = b2[H2],
    *             buf[4] = w3[H2], buf[5] = b3[1]            (torch [out,in] layout);
-   *             buf[6] = scratch workspace of ebm_mlp_workspace_bytes() bytes, 128-byte aligned, required by the
-   *             Langevin burst when D > 128 (the burst re-splits the weights into it at every call; one workspace
-   *             must not be shared by bursts running concurrently on different streams)   */
+   *             buf[6] = scratch workspace of ebm_mlp_workspace_bytes() bytes, 128-byte aligned, used by the
+   *             Langevin burst: hand-over flags of the balanced (tile, step-range) work split and, when D > 128,
+   *             the per-call bf16 hi/lo re-split of the weights.  Required when D > 128; optional (NULL = whole
+   *             tiles per SM, no balancing) when D <= 128.  One workspace must not be shared by bursts running
+   *             concurrently on different streams.   */
   const float* buf[8];
 } EbmEnergyDesc;
 

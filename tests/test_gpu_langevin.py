@@ -274,6 +274,34 @@ def test_wide_mlp_kernel_many_tiles_ragged_dims_trajectory(d, hidden, act):
     assert torch.equal(x1, a)
 
 
+def test_mlp_balanced_split_is_bit_identical_to_whole_tile_schedule():
+    """With a workspace the persistent MLP kernel splits a tile's K steps between two SMs (mlp_schedule.cuh); the
+    noise is counter based per (element, step), so the result must not depend on the split."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    torch.manual_seed(2)
+    model = te.MLPEnergy(dim=64, hidden=(96, 128), activation="silu").to(DEV)
+    n = 128 * 190 + 5   # 191 tiles on 148 SMs: most CTAs own a partial tile
+    x0 = torch.randn(n, 64, device=DEV).clamp_(-3, 3)
+    desc = te.energy_descriptor(model, 64, x0.device)
+    assert desc.c.buf[6]
+    traj_a = torch.empty(n, 2, 64, device=DEV)
+    a = ops.langevin_burst(desc, x0, 7, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=5, offset=8, traj=traj_a, thin=3)
+    desc.c.buf[6] = None
+    traj_b = torch.empty(n, 2, 64, device=DEV)
+    b = ops.langevin_burst(desc, x0, 7, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=5, offset=8, traj=traj_b, thin=3)
+    assert torch.equal(a, b) and torch.equal(traj_a, traj_b)
+    # a per-step schedule goes through the step-table path (several launches for K > 64)
+    hs = [0.01 * (0.99 ** i) for i in range(70)]
+    ns = [1.0] * 70
+    desc2 = te.energy_descriptor(model, 64, x0.device)
+    c = ops.langevin_burst(desc2, x0, 70, hs, ns, rng_mode=_lib.RNG_NATIVE, seed=5, offset=8)
+    desc2.c.buf[6] = None
+    d = ops.langevin_burst(desc2, x0, 70, hs, ns, rng_mode=_lib.RNG_NATIVE, seed=5, offset=8)
+    assert torch.equal(c, d)
+
+
 def test_x_none_draws_initial_state_from_generator():
     import torchebm_b200 as te
 

@@ -11,7 +11,8 @@ import threading
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libebm_b200.so")
+# EBM_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); still no fallback of any kind
+LIB_PATH = os.environ.get("EBM_B200_LIB") or os.path.join(HERE, "lib", "libebm_b200.so")
 
 EBM_ABI_VERSION = 3
 

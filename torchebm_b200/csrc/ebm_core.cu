@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "api_common.cuh"
+#include "mlp_schedule.cuh"
 
 namespace ebm {
 
@@ -292,7 +293,8 @@ int ebm_rng_fill_f32(float* out, int64_t numel, int32_t rng_mode, int32_t kind, 
 }
 
 int64_t ebm_mlp_workspace_bytes(const EbmEnergyDesc* e) {
-  if (!e || e->kind != EBM_ENERGY_MLP || e->dim <= 128) return 0;
+  if (!e || e->kind != EBM_ENERGY_MLP) return 0;
+  if (e->dim <= 128) return kMlpFlagBytes;  // hand-over flags of the balanced tile-step split (optional: buf[6] may be NULL)
   return (int64_t)mlp_wide_workspace_bytes(e);
 }
 

@@ -18,6 +18,7 @@
 //   MN-major backward descriptor), A hi+lo operand buffer, biases, barriers: 198 KB.
 #include "api_common.cuh"
 #include "umma.cuh"
+#include "mlp_schedule.cuh"
 #include <cuda_bf16.h>
 
 namespace ebm {
@@ -41,9 +42,10 @@ struct TcParams {
   const float* noise;
   float* traj;
   long long n;
-  int n_steps, thin, n_kept, thin_start, kept_base, has_clamp;
+  int n_steps, thin, n_kept, step_base, has_clamp;   // step_base: steps of this burst done by earlier launches
   float clamp_lo, clamp_hi;
   RowRng rng;
+  MlpSchedule sched;  // balanced (tile, step-range) split, mlp_schedule.cuh
 };
 
 struct TcSmemLayout {
@@ -58,7 +60,8 @@ struct TcSmemLayout {
   static constexpr int w3 = b2 + kTcW * 4;
   static constexpr int bars = w3 + kTcW * 4;           // kTcChunks + 1 mbarriers
   static constexpr int tmem_slot = bars + (kTcChunks + 1) * 8;
-  static constexpr int total = tmem_slot + 16;
+  static constexpr int units = tmem_slot + 16;
+  static constexpr int total = units + 16;
 };
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -209,20 +212,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     mbar_init(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8), 1);
     fence_mbar_init();
   }
+  if (threadIdx.x == 32) mlp_units_compute(P.sched, P.n_steps, reinterpret_cast<volatile MlpUnits*>(smem + TcSmemLayout::units));
   if (warp == 0) tmem_alloc(smem_u32(smem + TcSmemLayout::tmem_slot), 512);
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + TcSmemLayout::tmem_slot);
-  const long long n_tiles = (P.n + kTcM - 1) / kTcM;
   const int k1 = (P.d + 15) / 16, k2 = (P.h1 + 15) / 16, k3 = (P.h2 + 15) / 16;
+  const volatile MlpUnits* units = reinterpret_cast<const volatile MlpUnits*>(smem + TcSmemLayout::units);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t parity = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int k = 0; k < P.n_steps; ++k) {
+      for (int tile = units->t_last; tile >= units->t_first; --tile) {
+        const int n_unit_steps = mlp_unit_s1(units, tile, P.n_steps) - mlp_unit_s0(units, tile);
+        for (int k = 0; k < n_unit_steps; ++k) {
           tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity); parity ^= 1;
           tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity); parity ^= 1;
           tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity); parity ^= 1;
@@ -247,22 +252,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     const bool quad_rng = (P.d % 4 == 0);
     uint32_t parity = 0;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long grow = tile * kTcM + row;
+    for (int tile = units->t_last; tile >= units->t_first; --tile) {
+      const long long grow = (long long)tile * kTcM + row;
       const bool rv = grow < P.n;
+      const int s0 = mlp_unit_s0(units, tile), s1 = mlp_unit_s1(units, tile, P.n_steps);
+      // a unit that starts mid-burst continues the chain another CTA left in x_out
+      if (s0 > 0) mlp_unit_acquire(P.sched, kTcEpiWarps);
+      const float* x0src = (s0 == 0) ? P.x_in : P.x_out;
       float x[kTcCols];
 #pragma unroll
       for (int i = 0; i < kTcCols; ++i) {
         const int col = col_base + i;
-        x[i] = (rv && col < P.d) ? P.x_in[grow * P.d + col] : 0.0f;
+        x[i] = (rv && col < P.d) ? x0src[grow * P.d + col] : 0.0f;
       }
       store_a_cols(smem, row, col_base, x, with_lo);
       signal_cols(smem, first_chunk, lane);
-      int until_keep = P.thin_start, kept = P.kept_base;
+      int until_keep = P.thin - ((P.step_base + s0) % P.thin), kept = (P.step_base + s0) / P.thin;
       RngStream rs;
-      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = P.rng.ctr_base;
+      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode;
+      rs.ctr_base = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
 
-      for (int k = 0; k < P.n_steps; ++k) {
+      for (int k = s0; k < s1; ++k) {
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM columns [256, 384)
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
         // E4: g -> Langevin update of x; the new x is the A operand of the next step's GEMM1
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
-        const bool last = (k == P.n_steps - 1);
+        const bool last = (k == s1 - 1);
         bool keep_now = false;
         if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
 #pragma unroll
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
         for (int i = 0; i < kTcCols; ++i)
           if (col_base + i < P.d) P.x_out[grow * P.d + col_base + i] = x[i];
       }
+      if (s1 < P.n_steps) mlp_unit_release(P.sched);  // the rest of this tile's burst runs on the next CTA
     }
   }
   tcgen05_fence_before();
@@ -405,8 +416,9 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.rng.k0 = (uint32_t)c.seed ^ kNativeTag0; P.rng.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
     P.rng.ctr_step = 1;
   }
-  long long tiles = (c.n + kTcM - 1) / kTcM;
+  const long long tiles = (c.n + kTcM - 1) / kTcM;
   const int grid = (int)(tiles < di.sm_count ? tiles : di.sm_count);
+  int* flags = reinterpret_cast<int*>(const_cast<float*>(e->buf[6]));  // NULL: whole tiles per CTA (no balancing)
   const bool uniform = c.schedule_len == 1;
   int done = 0;
   const float* src = c.x_in;
@@ -421,8 +433,13 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.n_steps = chunk;
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;
-    P.thin_start = c.thin - (done % c.thin);
-    P.kept_base = done / c.thin;
+    P.step_base = done;
+    if (flags) {
+      int rc0 = mlp_schedule_setup(P.sched, tiles, chunk, grid, flags, c.st);
+      if (rc0) return rc0;
+    } else {
+      mlp_schedule_whole_tiles(P.sched, tiles, chunk, grid);
+    }
 #define CALL(A)                                                                                               \
   {                                                                                                           \
     auto kern = langevin_mlp_tc_kernel<A>;                                                                    \

@@ -15,11 +15,13 @@
 // (K-major view), the forward product z1 += x'_c . W1_c^T of step k+1 as soon as the epilogue has turned G_c into the
 // updated state chunk x'_c.  Per step and tile:
 //     [E1 -> GEMM2 -> E2 -> GEMM3 -> E3]   then for c in chunks: GEMM4_c -> E4_c (update, RNG, store x) -> GEMM1'_c
-// Warp roles: warp 0 = TMEM allocation + single-thread MMA issue, warp 1 = bulk-copy producer, warps 2..17 = epilogue
+// Warp roles: warp 0 = TMEM allocation + single-thread MMA issue, warp 1 = bulk-copy producer, warps 2-3 idle (they
+// complete the role warpgroup that gives its registers away), warps 4..19 = epilogue
 // (thread = one chain row x 32 hidden columns in the 128-wide phases, x 16 state columns per chunk in the E4 phase).
 // TMEM columns: [0,128) z1 / t, [128,256) z2, [256,384) act'(z1), [384,448) G even chunks, [448,512) G odd chunks.
 #include "api_common.cuh"
 #include "umma.cuh"
+#include "mlp_schedule.cuh"
 #include <cuda_bf16.h>
 
 namespace ebm {
@@ -33,7 +35,13 @@ constexpr int kWdStageBytes = 32768;    // ring item: W1 chunk hi (16 KB) + lo (
 constexpr int kWdHalf = 16384;
 constexpr int kWdStages = 3;
 constexpr int kWdEpiWarps = 16;
-constexpr int kWdThreads = 32 * (2 + kWdEpiWarps);
+constexpr int kWdRoleWarps = 4;         // one warpgroup: MMA issue, bulk-copy producer, two idle warps (setmaxnreg works per warpgroup)
+constexpr int kWdThreads = 32 * (kWdRoleWarps + kWdEpiWarps);
+// Register budget: 640 threads launch with 96 registers each; the role warpgroup shrinks to kWdRoleRegs and the four
+// epilogue warpgroups grow to kWdEpiRegs (128 * 32 + 512 * 112 = 640 * 96), which is what keeps the update epilogue
+// (48 live values + Philox state) out of local memory.
+constexpr int kWdRoleRegs = 32;
+constexpr int kWdEpiRegs = 112;
 constexpr int kWdMaxDim = 4096;
 
 struct WdSmem {
@@ -56,7 +64,8 @@ struct WdSmem {
   static constexpr int acc_full = a_chunk + 8;        // tcgen05.commit
   static constexpr int n_bars = acc_full + 1;
   static constexpr int tmem_slot = bars + n_bars * 8;
-  static constexpr int total = tmem_slot + 16;
+  static constexpr int units = tmem_slot + 16;
+  static constexpr int total = units + 16;
 };
 static_assert(WdSmem::total <= 232448, "shared memory budget of one sm_100 CTA exceeded");
 
@@ -70,9 +79,10 @@ struct WdParams {
   const float* noise;
   float* traj;
   long long n;
-  int n_steps, thin, n_kept, thin_start, kept_base, has_clamp;
+  int n_steps, thin, n_kept, step_base, has_clamp;   // step_base: steps of this burst done by earlier launches
   float clamp_lo, clamp_hi;
   RowRng rng;
+  MlpSchedule sched;
 };
 
 __device__ __forceinline__ uint32_t wd_bar(uint8_t* smem, int idx) { return smem_u32(smem + WdSmem::bars + idx * 8); }
@@ -284,17 +294,21 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     mbar_init(wd_bar(smem, WdSmem::acc_full), 1);
     fence_mbar_init();
   }
+  if (threadIdx.x == 32) mlp_units_compute(P.sched, P.n_steps, reinterpret_cast<volatile MlpUnits*>(smem + WdSmem::units));
   if (warp == 0) tmem_alloc(smem_u32(smem + WdSmem::tmem_slot), 512);
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + WdSmem::tmem_slot);
-  const long long n_tiles = (P.n + kWdM - 1) / kWdM;
   const int NC = P.nc;
   const int K = P.n_steps;
   const int k_h1 = (P.h1 + 15) / 16, k_h2 = (P.h2 + 15) / 16;
+  // this CTA's contiguous range of (tile, step) work, walked from its last tile to its first (mlp_schedule.cuh)
+  const volatile MlpUnits* units = reinterpret_cast<const volatile MlpUnits*>(smem + WdSmem::units);
 
+  if (warp < kWdRoleWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWdRoleRegs));
   if (warp == 1) {
     // ---- producer: stream the weight blobs through the ring in the fixed item order --------------------------
     if (lane == 0) {
@@ -309,9 +323,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         bulk_g2s(smem_u32(smem + WdSmem::ring + s * kWdStageBytes), src, kWdStageBytes, full);
         ++it;
       };
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = units->t_last; tile >= units->t_first; --tile) {
         for (int c = 0; c < NC; ++c) push(P.ws + (size_t)c * kWdStageBytes);
-        for (int k = 0; k < K; ++k) {
+        const int n_unit_steps = mlp_unit_s1(units, tile, K) - mlp_unit_s0(units, tile);
+        for (int k = 0; k < n_unit_steps; ++k) {
           push(w2hi);
           push(w2lo);
           for (int c = 0; c < NC; ++c) push(P.ws + (size_t)c * kWdStageBytes);
@@ -370,8 +385,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         a_par ^= 1;
       };
 
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < NC; ++c) {  // prologue: z1 of the initial state
+      for (int tile = units->t_last; tile >= units->t_first; --tile) {
+        const int n_unit_steps = mlp_unit_s1(units, tile, K) - mlp_unit_s0(units, tile);
+        for (int c = 0; c < NC; ++c) {  // prologue: z1 of the unit's initial state
           ring_wait(it);
           xa_wait();
           gemm1_chunk(it, c);
@@ -380,8 +396,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           ++it;
         }
         mma_commit(wd_bar(smem, WdSmem::acc_full));
-        for (int k = 0; k < K; ++k) {
-          const bool last = (k == K - 1);
+        for (int k = 0; k < n_unit_steps; ++k) {
+          const bool last = (k == n_unit_steps - 1);
           ring_wait(it);
           ring_wait(it + 1);
           const uint32_t w2hi = stage_addr(it), w2lo = stage_addr(it + 1);
@@ -413,9 +429,11 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       // the last commits must have landed in shared memory before the CTA may retire
       if (it > 0) mbar_wait(wd_bar(smem, WdSmem::ring_empty + (it - 1) % kWdStages), ((it - 1) / kWdStages) & 1);
     }
+  }
   } else {
     // ---- epilogue warps -------------------------------------------------------------------------------------------
-    const int e = warp - 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWdEpiRegs));
+    const int e = warp - kWdRoleWarps;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access (hardware: warp % 4)
     const int cg = e >> 2;                          // column group 0..3
     const int row = 32 * q + lane;
@@ -437,14 +455,18 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     const long long numel = P.n * P.d;
     uint32_t acc_par = 0, g_par = 0;  // g_par: bit b = parity of g_full[b]
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long grow = tile * kWdM + row;
+    for (int tile = units->t_last; tile >= units->t_first; --tile) {
+      const long long grow = (long long)tile * kWdM + row;
       const bool rv = grow < P.n;
-      // prologue: publish the initial state chunk by chunk
+      const int s0 = mlp_unit_s0(units, tile), s1 = mlp_unit_s1(units, tile, K);
+      // a unit that starts mid-burst continues the chain another CTA left in x_out
+      if (s0 > 0) mlp_unit_acquire(P.sched, kWdEpiWarps);
+      const float* x0src = (s0 == 0) ? P.x_in : P.x_out;
+      // prologue: publish the unit's initial state chunk by chunk
       for (int c = 0; c < NC; ++c) {
         const int col0 = c * kWdChunk + 16 * cg;
         float v[16];
-        wd_load_x16(P.x_in, grow, col0, P.d, rv, vec, v);
+        wd_load_x16(x0src, grow, col0, P.d, rv, vec, v);
         const uint32_t xb = xcnt & 1;
         mbar_wait(xa_empty + 8 * xb, ((xcnt >> 1) & 1) ^ 1);
         ++xcnt;
@@ -452,11 +474,12 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         if (col0 < P.d) wd_store16(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, v, with_lo);
         wd_publish(xa_full + 8 * xb);
       }
-      int until_keep = P.thin_start, kept = P.kept_base;
+      int until_keep = P.thin - ((P.step_base + s0) % P.thin), kept = (P.step_base + s0) / P.thin;
       RngStream rs;
-      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = P.rng.ctr_base;
+      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode;
+      rs.ctr_base = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
 
-      for (int k = 0; k < K; ++k) {
+      for (int k = s0; k < s1; ++k) {
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
         const float* xsrc = (k == 0) ? P.x_in : P.x_out;
@@ -576,6 +599,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         }
         rs.ctr_base += P.rng.ctr_step;
       }
+      if (s1 < K) mlp_unit_release(P.sched);  // the rest of this tile's burst runs on the next CTA
     }
   }
   tcgen05_fence_before();
@@ -787,10 +811,11 @@ int mlp_wide_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_
   return launch_status("mlp_wide_energy_grad_kernel");
 }
 
-size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e) {
+static size_t mlp_wide_weight_bytes(const EbmEnergyDesc* e) {
   const int nc = (e->dim + kWdChunk - 1) / kWdChunk;
   return (size_t)(nc + 2) * kWdStageBytes;
 }
+size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e) { return mlp_wide_weight_bytes(e) + kMlpFlagBytes; }
 
 bool mlp_wide_supported(const EbmEnergyDesc* e) {
   return e->dim <= kWdMaxDim && e->hidden1 <= kWdH && e->hidden2 <= kWdH;
@@ -841,8 +866,9 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     int rc = launch_status("mlp_wide_prep_kernel");
     if (rc) return rc;
   }
-  long long tiles = (c.n + kWdM - 1) / kWdM;
+  const long long tiles = (c.n + kWdM - 1) / kWdM;
   const int grid = (int)(tiles < di.sm_count ? tiles : di.sm_count);
+  int* flags = reinterpret_cast<int*>(const_cast<float*>(e->buf[6])) + mlp_wide_weight_bytes(e) / 4;
   const bool uniform = c.schedule_len == 1;
   int done = 0;
   const float* src = c.x_in;
@@ -857,8 +883,9 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     P.n_steps = chunk;
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;
-    P.thin_start = c.thin - (done % c.thin);
-    P.kept_base = done / c.thin;
+    P.step_base = done;
+    int rc0 = mlp_schedule_setup(P.sched, tiles, chunk, grid, flags, c.st);
+    if (rc0) return rc0;
 #define CALL(A)                                                                                            \
   {                                                                                                        \
     auto kern = langevin_mlp_wide_kernel<A>;                                                               \

@@ -1,0 +1,87 @@
+// Balanced work split of the persistent MLP Langevin kernels.
+//
+// A burst is `tiles` x `K` tile-steps (tile = 128 chains, one Langevin step).  Handing out whole tiles leaves
+// ceil(tiles / SMs) rounds of work on some SMs and one round less on the others (65 536 chains = 512 tiles on 148 SMs:
+// 4 rounds for 3.46 rounds of work).  Instead every CTA gets a contiguous range of the linearised (tile-major)
+// tile-step sequence, equal to within one tile-step, so a tile's K steps may be split between CTA b-1 (its first
+// steps) and CTA b (the rest).  Because tiles > CTAs whenever anything is split, a range is longer than K: a tile
+// spans at most two CTAs.  Each CTA walks its range from its LAST tile to its FIRST, so the shared tile's head is
+// the first thing CTA b-1 does and its tail the last thing CTA b does: the hand-over (chain state through x_out in
+// global memory, one release/acquire flag per CTA) is never waited on for long and cannot deadlock -- the head unit
+// of any CTA depends on nothing.  The RNG is counter based per (element, step), so results do not depend on the split.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ebm {
+
+constexpr int kMlpFlagBytes = 1024;  // one int per CTA (grid <= number of SMs <= 256)
+
+struct MlpSchedule {
+  long long quota;  // work quanta per CTA (floor)
+  int rem;          // the first `rem` CTAs take one quantum more
+  int gran;         // tile-steps per quantum: 1 = balanced split, K = whole tiles only (no hand-over, no flags needed)
+  int* flags;       // [grid], zeroed before the launch; flags[b] counts epilogue warps of CTA b done with its head unit
+};
+
+// The CTA's range, reduced to four ints that live in shared memory (not in registers across the hot loops):
+// tiles [t_first, t_last], first tile from step first_s0, last tile up to step last_s1.
+struct MlpUnits {
+  int t_first, t_last, first_s0, last_s1;
+};
+__device__ __forceinline__ void mlp_units_compute(const MlpSchedule& s, int K, volatile MlpUnits* u) {
+  const long long b = blockIdx.x;
+  const long long lin_begin = (b * s.quota + (b < s.rem ? b : s.rem)) * s.gran;
+  const long long lin_end = lin_begin + (s.quota + (b < s.rem ? 1 : 0)) * s.gran;
+  const long long tf = lin_begin / K, tl = (lin_end - 1) / K;
+  u->t_first = (int)tf;
+  u->t_last = (int)tl;
+  u->first_s0 = (int)(lin_begin - tf * K);
+  u->last_s1 = (int)(lin_end - tl * K);
+}
+// steps [s0, s1) of `tile` that belong to this CTA
+__device__ __forceinline__ int mlp_unit_s0(const volatile MlpUnits* u, int tile) { return tile == u->t_first ? u->first_s0 : 0; }
+__device__ __forceinline__ int mlp_unit_s1(const volatile MlpUnits* u, int tile, int K) { return tile == u->t_last ? u->last_s1 : K; }
+
+// called by every epilogue warp (all lanes) after its last global store of a head unit
+__device__ __forceinline__ void mlp_unit_release(const MlpSchedule& s) {
+  __threadfence();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) atomicAdd(s.flags + blockIdx.x, 1);
+}
+// called by every epilogue warp (all lanes) before its first global load of a tail unit
+__device__ __forceinline__ void mlp_unit_acquire(const MlpSchedule& s, int n_warps) {
+  if ((threadIdx.x & 31) == 0) {
+    const int* f = s.flags + (blockIdx.x - 1);
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v < n_warps) __nanosleep(200);
+    } while (v < n_warps);
+  }
+  __syncwarp();
+}
+
+// host: fill the schedule for `tiles` x `k_steps` on `grid` CTAs and zero the flags on the stream
+inline int mlp_schedule_setup(MlpSchedule& s, long long tiles, int k_steps, int grid, int* flags, cudaStream_t st) {
+  const long long total = tiles * (long long)k_steps;
+  s.quota = total / grid;
+  s.rem = (int)(total % grid);
+  s.gran = 1;
+  s.flags = flags;
+  if (tiles > grid) {  // only then can a tile be shared by two CTAs
+    cudaError_t err = cudaMemsetAsync(flags, 0, kMlpFlagBytes, st);
+    if (err != cudaSuccess) return (int)err;
+  }
+  return 0;
+}
+
+// host: no flag memory available -> every CTA takes whole tiles only (contiguous blocks of tiles; no hand-over)
+inline void mlp_schedule_whole_tiles(MlpSchedule& s, long long tiles, int k_steps, int grid) {
+  s.quota = tiles / grid;
+  s.rem = (int)(tiles % grid);
+  s.gran = k_steps;
+  s.flags = nullptr;
+}
+
+}  // namespace ebm
