@@ -7,8 +7,9 @@
 // the largest term; the dropped lo*lo term is ~2^-18).  precision == EBM_MLP_BF16 skips the two correction passes.
 //
 // One CTA = one tile of 128 chains (TMEM lane = chain), persistent over tiles, resident for all K steps:
-//   warp 0      : allocates TMEM, then one elected lane issues every MMA and commits to an mbarrier;
-//   warps 1..8  : epilogue.  Thread = (row r = TMEM lane, column half); x[r, 64 cols] lives in its registers.
+//   warp 0      : allocates TMEM, then one elected lane issues every MMA and commits to an mbarrier (warps 1-3 idle:
+//                 they complete the warpgroup that hands its registers to the epilogue via setmaxnreg);
+//   warps 4..19 : epilogue.  Thread = (row r = TMEM lane, column quarter); x[r, 32 cols] lives in its registers.
 // Per step and tile the dependency chain is GEMM1 -> E1 -> GEMM2 -> E2 -> GEMM3 -> E3 -> GEMM4 -> E4(update) -> GEMM1'.
 // Each epilogue produces the A operand of the NEXT product in 16-column chunks (= one MMA k-step) and signals a
 // per-chunk mbarrier, so the MMA of product n+1 runs underneath epilogue n; the tensor pipe is hidden behind the
@@ -30,7 +31,18 @@ constexpr int kTcW = 128;          // padded width of every layer
 constexpr int kTcChunks = kTcW / 16;
 constexpr int kTcEpiWarps = 16;         // 4 lane quarters x 4 column quarters
 constexpr int kTcCols = kTcW / (kTcEpiWarps / 4);  // columns per epilogue thread (32)
-constexpr int kTcThreads = 32 * (1 + kTcEpiWarps);
+constexpr int kTcRoleWarps = 4;          // one warpgroup: warp 0 issues the MMAs, warps 1-3 idle (setmaxnreg works per warpgroup)
+constexpr int kTcThreads = 32 * (kTcRoleWarps + kTcEpiWarps);
+// 640 threads launch with 96 registers each; optionally the role warpgroup shrinks and the four epilogue warpgroups grow
+// (e.g. 128 * 32 + 512 * 112 = 640 * 96)
+#ifndef EBM_TC_ROLE_REGS
+// measured on B200 (tools/mlp_probe.py): 96/96 (no rebalance) 14.95 us per tile-step, 56/104 15.3, 32/112 15.9 -- here the
+// issue latency of the MMA thread matters more than the epilogue's few spills, so the default leaves the budget alone
+#define EBM_TC_ROLE_REGS 96
+#define EBM_TC_EPI_REGS 96
+#endif
+constexpr int kTcRoleRegs = EBM_TC_ROLE_REGS;
+constexpr int kTcEpiRegs = EBM_TC_EPI_REGS;
 constexpr int kTcMatBytes = kTcW * kTcW * 2;  // one bf16 [128 x 128] operand
 
 struct TcParams {
@@ -128,12 +140,12 @@ __device__ __forceinline__ void signal_cols(uint8_t* smem, int first_chunk, int 
 template <int ACT>
 __device__ __forceinline__ void act_fast(float z, float& h, float& dh) {
   if (ACT == EBM_ACT_SILU) {
-    const float s = __frcp_rn(1.0f + __expf(-z));
+    const float s = rcp_fast(1.0f + __expf(-z));
     h = z * s;
     dh = s * (1.0f + z * (1.0f - s));
   } else if (ACT == EBM_ACT_TANH) {
     const float e = __expf(-2.0f * fabsf(z));
-    const float t = copysignf((1.0f - e) * __frcp_rn(1.0f + e), z);
+    const float t = copysignf((1.0f - e) * rcp_fast(1.0f + e), z);
     h = t;
     dh = 1.0f - t * t;
   } else if (ACT == EBM_ACT_RELU) {
@@ -141,7 +153,7 @@ __device__ __forceinline__ void act_fast(float z, float& h, float& dh) {
     dh = z > 0.0f ? 1.0f : 0.0f;
   } else {
     h = z > 20.0f ? z : log1pf(__expf(z));
-    dh = __frcp_rn(1.0f + __expf(-z));
+    dh = rcp_fast(1.0f + __expf(-z));
   }
 }
 
@@ -222,8 +234,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
   const int k1 = (P.d + 15) / 16, k2 = (P.h1 + 15) / 16, k3 = (P.h2 + 15) / 16;
   const volatile MlpUnits* units = reinterpret_cast<const volatile MlpUnits*>(smem + TcSmemLayout::units);
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < kTcRoleWarps) {
+    if (kTcRoleRegs < 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcRoleRegs));
+    if (warp == 0 && lane == 0) {
       uint32_t parity = 0;
       for (int tile = units->t_last; tile >= units->t_first; --tile) {
         const int n_unit_steps = mlp_unit_s1(units, tile, P.n_steps) - mlp_unit_s0(units, tile);
@@ -237,7 +250,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     }
   } else {
     // ---- epilogue warps -------------------------------------------------------------------------
-    const int e = warp - 1;
+    if (kTcEpiRegs > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
+    const int e = warp - kTcRoleWarps;
     const int row = 32 * (warp & 3) + lane;        // TMEM lane this thread may access (hardware: warp % 4)
     const int cq = e >> 2;                          // column quarter
     const int col_base = kTcCols * cq;

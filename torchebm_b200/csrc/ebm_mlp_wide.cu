@@ -176,12 +176,12 @@ __device__ __forceinline__ void wd_publish(uint32_t bar) {
 template <int ACT>
 __device__ __forceinline__ void wd_act(float z, float& h, float& dh) {
   if (ACT == EBM_ACT_SILU) {
-    const float s = __frcp_rn(1.0f + __expf(-z));
+    const float s = rcp_fast(1.0f + __expf(-z));
     h = z * s;
     dh = s * (1.0f + z * (1.0f - s));
   } else if (ACT == EBM_ACT_TANH) {
     const float e = __expf(-2.0f * fabsf(z));
-    const float t = copysignf((1.0f - e) * __frcp_rn(1.0f + e), z);
+    const float t = copysignf((1.0f - e) * rcp_fast(1.0f + e), z);
     h = t;
     dh = 1.0f - t * t;
   } else if (ACT == EBM_ACT_RELU) {
@@ -189,7 +189,7 @@ __device__ __forceinline__ void wd_act(float z, float& h, float& dh) {
     dh = z > 0.0f ? 1.0f : 0.0f;
   } else {
     h = z > 20.0f ? z : log1pf(__expf(z));
-    dh = __frcp_rn(1.0f + __expf(-z));
+    dh = rcp_fast(1.0f + __expf(-z));
   }
 }
 

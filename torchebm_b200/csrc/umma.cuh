@@ -142,4 +142,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 }  // namespace umma
+
+// single MUFU.RCP (1 ulp); the IEEE-rounded __frcp_rn costs a Newton fix-up the activations do not need
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 }  // namespace ebm
