@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the fused MCMC negative-sampling hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|mlp128|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5|mlp128]
 
 One bench "step" = one pass of the hot path over one batch: a K-step fused burst through the sampler-level
 API (`ops.langevin_burst` / `ops.hmc_burst`, i.e. one C-ABI call, one kernel launch).  Headline workload =
@@ -40,7 +40,11 @@ WORKLOADS = {
     "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
     "c3": ("ContrastiveDivergence persistent=True negatives: replay-buffer gather -> LangevinDynamics MLP 784-128-128-1 SiLU "
            "k=20 step_size=0.01 -> FIFO write-back; n_chains=65536=buffer_size", 65536, 784, 20),
+    # C5 = C3 sharded over the GPUs of one box: 65 536 chains PER GPU (524 288 at 8 GPUs), weak scaling
+    "c5": ("Persistent-CD negatives (as c3), MLP 784-128-128-1, 65536 chains per GPU sharded on the chain axis, "
+           "NCCL all-gather of the negatives at burst end", 65536, 784, 20),
 }
+WEAK = {"c5"}
 METRIC = "langevin_chain_steps_per_sec"
 UNIT = "chain-steps/s"
 
@@ -126,7 +130,8 @@ def dist_setup(n_gpus: int):
 
 
 def make_workload(name: str, n_local: int, dev):
-    """Returns (step_fn(x_in, out, it, kev) -> launches, desc, model, algorithmic bytes per chain-step, units per chain).
+    """Returns (step_fn(x_in, out, it, kev) -> (launches, result tensor), desc, model, algorithmic bytes per chain-step,
+    units per chain).
     `kev` = (start, end) CUDA events the step records around its dominant kernel (None: do not record)."""
     import torchebm_b200 as te
     from torchebm_b200 import _lib, ops
@@ -141,7 +146,7 @@ def make_workload(name: str, n_local: int, dev):
             if kev: kev[0].record()
             ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
             if kev: kev[1].record()
-            return 1
+            return 1, out
 
         return step, desc, model, 8 * d, k
     if name.startswith("mlp128"):
@@ -155,7 +160,7 @@ def make_workload(name: str, n_local: int, dev):
             if kev: kev[0].record()
             ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=1234, offset=it * inc, out=out)
             if kev: kev[1].record()
-            return 1
+            return 1, out
 
         return step, desc, model, 8 * d, k
     if name == "c4":
@@ -167,10 +172,10 @@ def make_workload(name: str, n_local: int, dev):
             if kev: kev[0].record()
             ops.hmc_burst(desc, x, 1, k, [0.01], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
             if kev: kev[1].record()
-            return 1
+            return 1, out
 
         return step, desc, model, 16 * d, k
-    if name == "c3":
+    if name in ("c3", "c5"):
         torch.manual_seed(0)
         model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev)
         sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=dev, rng="native")
@@ -187,7 +192,7 @@ def make_workload(name: str, n_local: int, dev):
             neg = sampler.sample(x=start, n_steps=k, generator=gen)
             if kev: kev[1].record()
             cd.update_buffer(neg)
-            return 4  # pcd_gather, mlp_wide_prep, langevin_mlp_wide, pcd_scatter
+            return 4, neg  # pcd_gather, mlp_wide_prep, langevin_mlp_wide, pcd_scatter
 
         return step, desc, model, 8 * d, k
     raise KeyError(name)
@@ -203,22 +208,28 @@ def run_ours(args):
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     desc_text, n_total, d, k = WORKLOADS[args.workload]
+    if args.workload in WEAK:
+        n_total *= world
     lo, hi = shard_bounds(n_total, rank, world)
     n_local = hi - lo
     step, desc, model, bytes_per_unit, units_per_chain = make_workload(args.workload, n_local, dev)
 
     # synthetic particle batch: N(0,1) truncated to +-3 so every chain starts inside the stability region of the
     # explicit step (|x| < 5 at h = 0.01 for DoubleWell); the reference diverges to NaN outside it as well
-    x_full = torch.randn(n_total, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
-    x_local = x_full[lo:hi].to(dev)
+    if args.workload in WEAK:  # every rank draws only its own shard (seed + rank)
+        x_full = None
+        x_local = torch.randn(hi - lo, d, generator=torch.Generator().manual_seed(rank)).clamp_(-3.0, 3.0).to(dev)
+    else:
+        x_full = torch.randn(n_total, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
+        x_local = x_full[lo:hi].to(dev)
     out_local = torch.empty_like(x_local)
     gathered = torch.empty(n_total, d, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def one_step(it):
-        n = step(x_local, out_local, it)
+        n, res = step(x_local, out_local, it)
         if world > 1:
-            gather_chains(out_local, out=gathered)
+            gather_chains(res, out=gathered)
         return n
 
     def barrier():
@@ -240,9 +251,10 @@ def run_ours(args):
         for it in range(args.steps):
             flush.zero_()  # evict the state from L2 between timed iterations (not timed)
             starts[it].record()
-            launches += step(x_local, out_local, args.warmup + it, (kstarts[it], kends[it]))
+            n_l, res = step(x_local, out_local, args.warmup + it, (kstarts[it], kends[it]))
+            launches += n_l
             if world > 1:
-                gather_chains(out_local, out=gathered)
+                gather_chains(res, out=gathered)
             ends[it].record()
         barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
@@ -303,10 +315,11 @@ def run_ours(args):
     line = {
         "metric": METRIC if args.workload != "c4" else "hmc_leapfrog_chain_steps_per_sec",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong",
+        "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc_text,
-                   "rng": ("native-layout" if args.workload.startswith("mlp128") or args.workload == "c3" else "torch-layout") + " Philox4x32-10 drawn in-kernel",
+                   "rng": ("native-layout" if args.workload.startswith("mlp128") or args.workload in ("c3", "c5") else "torch-layout") + " Philox4x32-10 drawn in-kernel",
                    "chains_per_gpu": n_local, "collective": "all_gather of [N/W, D] shards at burst end" if world > 1 else "none",
                    "l2": "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events"},
         "e2e": e2e,
@@ -328,8 +341,8 @@ def run_ours(args):
 def roofline(workload, peaks, peak_kind, achieved_gbs, traffic, algo_bytes, kernel_ms, units_per_launch):
     """HBM streaming model for the analytic paths; tensor-pipe model (4*(D*H + H*H + H) FLOP per chain-step,
     against the measured bf16 burst peak) for the MLP path."""
-    if workload.startswith("mlp128") or workload == "c3":
-        d_in = 784 if workload == "c3" else 128
+    if workload.startswith("mlp128") or workload in ("c3", "c5"):
+        d_in = 784 if workload in ("c3", "c5") else 128
         flops = 4 * (d_in * 128 + 128 * 128 + 128) * units_per_launch
         ach = flops / (kernel_ms * 1e-3) / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -346,7 +359,7 @@ def _oracle_energy(workload, device="cpu"):
 
     if workload.startswith("mlp128"):
         return E.make_mlp(128, (128, 128), "silu", seed=0).to(device)
-    if workload == "c3":
+    if workload in ("c3", "c5"):
         return E.make_mlp(784, (128, 128), "silu", seed=0).to(device)
     return E.DoubleWell(2.0, 1.0)
 
@@ -393,13 +406,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    desc_text, n, d, k = WORKLOADS["c2"]
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is one CPU job that may use the whole host
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = args.workload if args.workload in ("c2", "c3", "c5", "mlp128") else "c2"
+    desc_text, n, d, k = WORKLOADS[wl]
     from oracle import langevin as olang
 
-    en = _oracle_energy("c2")
+    en = _oracle_energy(wl)
     x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
     gen = torch.Generator().manual_seed(1)
-    ks = args.cpu_k
+    ks = args.cpu_k if wl == "c2" else 2
     for _ in range(args.warmup):
         olang.sample(en, x0, ks, 0.01, 1.0, generator=gen)
     t0 = time.perf_counter()
