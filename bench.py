@@ -186,13 +186,13 @@ def make_workload(name: str, n_local: int, dev):
 
         def step(x, out, it, kev=None):
             # the sampling half of ContrastiveDivergence.forward (losses/contrastive_divergence.py:127-139): start points
-            # from the replay buffer, K-step negative chain, FIFO write-back.  The loss/backward is the training objective.
-            start = cd.get_start_points(x, generator=gen)
+            # from the replay buffer, K-step negative chain, FIFO write-back -- one library call here (buffer_size ==
+            # batch: the burst kernel reads its start rows from the buffer and writes the final state back into it).
+            # The loss/backward is the training objective, not the sampling path.
             if kev: kev[0].record()
-            neg = sampler.sample(x=start, n_steps=k, generator=gen)
+            neg = cd.sample_negatives(x, generator=gen)
             if kev: kev[1].record()
-            cd.update_buffer(neg)
-            return 4, neg  # pcd_gather, mlp_wide_prep, langevin_mlp_wide, pcd_scatter
+            return 2, neg  # mlp_wide_prep_kernel, langevin_mlp_wide_kernel (+ torch's randint for the index draw)
 
         return step, desc, model, 8 * d, k
     raise KeyError(name)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 3
+#define EBM_ABI_VERSION 4
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -162,6 +162,19 @@ int ebm_pcd_gather_f32(const float* buffer, int64_t buffer_rows, int64_t row_ele
                        int64_t n_noise, void* stream);
 int ebm_pcd_scatter_f32(float* buffer, int64_t buffer_rows, int64_t row_elems, int64_t ptr,
                         const float* samples, int64_t batch, int64_t* new_ptr_host, void* stream);
+
+/* Persistent-CD negative sampling in one call: start points buffer[idx[i], :] (get_start_points without exploration
+ * noise, core/base_loss.py:293-314), n_steps Langevin steps into x_out[n, dim], FIFO write-back of x_out into the
+ * buffer at `ptr` (update_buffer, :390-426).  For energies with ebm_pcd_langevin_fused(e) != 0 the gather is the burst
+ * kernel's first load and, when n == buffer_rows (idx is then the identity by construction and the whole buffer is
+ * replaced), the write-back is its last store: no extra pass over the buffer.  Other energies run gather -> burst ->
+ * scatter and need `scratch` [n, dim].  Row length of the buffer = e->dim.  *new_ptr_host receives the new ptr. */
+int ebm_pcd_langevin_fused(const EbmEnergyDesc* e);
+int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
+                               int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
+                               const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                               const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                               int64_t* new_ptr_host, void* stream);
 
 /* Fill out[numel] with the TORCH- or NATIVE-layout normal (kind 0) / uniform (kind 1) stream at
  * (seed, offset): test hook that exposes exactly what the fused kernels draw. */

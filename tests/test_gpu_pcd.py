@@ -124,3 +124,60 @@ def test_c3_shape_cd_step_runs_fused():
     loss, neg = cd(x, generator=torch.Generator(DEV).manual_seed(0))
     assert torch.isfinite(neg).all() and torch.isfinite(loss)
     loss.backward()
+
+
+@pytest.mark.parametrize("d,buffer_size,batch", [(784, 300, 300), (784, 700, 300), (64, 33000, 33000), (64, 40000, 4096),
+                                                  (64, 100, 300)])
+@pytest.mark.parametrize("rng", ["torch", "native"])
+def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rng):
+    """`sample_negatives` (one library call: start rows read through the index inside the burst kernel, final state
+    written straight back into the buffer when buffer_size == batch) must leave exactly the negatives, the buffer, the
+    FIFO pointer and the generator that get_start_points -> sample -> update_buffer leave."""
+    import warnings
+
+    import torchebm_b200 as te
+
+    torch.manual_seed(3)
+    model = te.MLPEnergy(dim=d, hidden=(128, 96), activation="silu").to(DEV)
+
+    def make():
+        sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV, rng=rng)
+        return te.ContrastiveDivergence(model, sampler, k_steps=4, persistent=True, buffer_size=buffer_size, init_steps=0,
+                                        new_sample_ratio=0.0, device=DEV)
+
+    a, b = make(), make()
+    ga, gb = torch.Generator(DEV).manual_seed(21), torch.Generator(DEV).manual_seed(21)
+    data = torch.randn(3, batch, d, device=DEV)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # buffer smaller than batch warns, like the reference
+        for it in range(3):
+            neg_a = a.sample_negatives(data[it], generator=ga)
+            start = b.get_start_points(data[it], generator=gb)
+            neg_b = b.sampler.sample(x=start, n_steps=4, generator=gb)
+            b.update_buffer(neg_b)
+            assert torch.equal(neg_a, neg_b)
+            assert torch.equal(a.replay_buffer, b.replay_buffer)
+            assert a._buffer_ptr_int == b._buffer_ptr_int and int(a.buffer_ptr) == int(b.buffer_ptr)
+            assert ga.get_offset() == gb.get_offset()
+
+
+def test_fused_pcd_falls_back_for_analytic_energies_and_matches_reference_golden():
+    """Energies without an index-reading kernel run gather -> burst -> scatter inside the same C call."""
+    import torchebm_b200 as te
+
+    g = C.load("pcd_doublewell_fifo")
+    model = te.DoubleWellModel(2.0, 1.0)
+    sampler = te.LangevinDynamics(model, step_size=0.01, device=DEV)
+    a = te.ContrastiveDivergence(model, sampler, k_steps=2, persistent=True, buffer_size=50, init_steps=0,
+                                 new_sample_ratio=0.0, device=DEV)
+    b = te.ContrastiveDivergence(model, te.LangevinDynamics(model, step_size=0.01, device=DEV), k_steps=2, persistent=True,
+                                 buffer_size=50, init_steps=0, new_sample_ratio=0.0, device=DEV)
+    ga, gb = torch.Generator(DEV).manual_seed(5), torch.Generator(DEV).manual_seed(5)
+    data = g["data"].to(DEV)
+    for it in range(data.shape[0]):
+        neg_a = a.sample_negatives(data[it], generator=ga)
+        start = b.get_start_points(data[it], generator=gb)
+        neg_b = b.sampler.sample(x=start, n_steps=2, generator=gb)
+        b.update_buffer(neg_b)
+        assert torch.equal(neg_a, neg_b) and torch.equal(a.replay_buffer, b.replay_buffer)
+        assert a._buffer_ptr_int == b._buffer_ptr_int == int(g["ptrs"][it])

@@ -508,7 +508,7 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         for i, t in enumerate(ts):
             d.buf[i] = t.data_ptr()
         ws_bytes = int(_lib.load().ebm_mlp_workspace_bytes(C.byref(d)))
-        if ws_bytes > 0:  # wide states: scratch for the per-burst bf16 hi/lo re-split of the weights
+        if ws_bytes > 0 and torch.device(device).type == "cuda":  # hand-over flags + (wide states) the bf16 weight re-split
             ws = _mlp_workspace(device, ws_bytes)
             d.buf[6] = ws.data_ptr()
             ts.append(ws)

@@ -154,6 +154,9 @@ struct LangevinCall {
   float* traj;
   int32_t thin;
   cudaStream_t st;
+  // persistent-CD fusion (ebm_pcd_langevin_burst_f32; MLP kernels only, NULL otherwise):
+  const long long* row_index;  // chain i starts from row row_index[i] of x_in (the replay buffer)
+  float* x_out2;               // the final state is also written here, row i -> row i (FIFO write-back when S == B)
 };
 
 inline int row_grid(const DeviceInfo& di, long long n, int G, int ctas_per_sm) {

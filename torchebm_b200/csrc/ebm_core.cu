@@ -358,8 +358,55 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
   EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
   EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
-                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream};
+                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr};
   return langevin_dispatch(c);
+}
+
+int ebm_pcd_langevin_fused(const EbmEnergyDesc* e) {
+  // the tensor-core MLP kernels read their start rows through an index and can write the final state twice
+  return e && e->kind == EBM_ENERGY_MLP && (e->precision == EBM_MLP_BF16X3 || e->precision == EBM_MLP_BF16) ? 1 : 0;
+}
+
+int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
+                               int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
+                               const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                               const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                               int64_t* new_ptr_host, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(buffer && idx && x_out && buffer_rows > 0 && n > 0, "buffer/idx/x_out must be non-null, sizes positive");
+  EBM_CHECK_ARG(ptr >= 0 && ptr < buffer_rows, "ptr out of range");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(step_size_host && noise_scale_host, "schedules must be non-null");
+  EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
+  EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "the fused PCD burst draws its own noise");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  const bool fused = ebm_pcd_langevin_fused(e) != 0;
+  EBM_CHECK_ARG(fused || scratch, "scratch [n, dim] is required for energies without a fused gather");
+  const int64_t row_elems = e->dim;
+  if (!fused) {  // gather -> burst -> FIFO scatter as three launches
+    rc = ebm_pcd_gather_f32(buffer, buffer_rows, row_elems, idx, n, scratch, nullptr, nullptr, 0, stream);
+    if (rc) return rc;
+    rc = ebm_langevin_burst_f32(e, scratch, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len,
+                                clamp_lo_hi_host, rng_mode, seed, offset, nullptr, nullptr, 1, stream);
+    if (rc) return rc;
+    return ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
+  }
+  // n == buffer_rows: the reference's stratified draw has stride 1, i.e. idx is the identity, and the write-back
+  // replaces the whole buffer with ptr = 0 (core/base_loss.py:307-312, :409-413): chain i reads and writes row i,
+  // so the final state can go to both destinations from inside the burst.  Otherwise rows are read through idx and
+  // the FIFO write-back stays a separate launch (a destination row may be another chain's source row).
+  const bool identity = (n == buffer_rows);
+  LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                 rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream,
+                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr};
+  rc = langevin_dispatch(c);
+  if (rc) return rc;
+  if (identity) {
+    if (new_ptr_host) *new_ptr_host = 0;
+    return 0;
+  }
+  return ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
 }
 
 int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, float* x_out_host, float* scratch_dev,

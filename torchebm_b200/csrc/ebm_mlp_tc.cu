@@ -53,6 +53,8 @@ struct TcParams {
   float* x_out;
   const float* noise;
   float* traj;
+  const long long* row_index;  // persistent-CD: source row of chain i in x_in (first launch of a burst only), or NULL
+  float* x_out2;               // persistent-CD: second destination of the burst's final state (last launch only), or NULL
   long long n;
   int n_steps, thin, n_kept, step_base, has_clamp;   // step_base: steps of this burst done by earlier launches
   float clamp_lo, clamp_hi;
@@ -273,11 +275,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
       // a unit that starts mid-burst continues the chain another CTA left in x_out
       if (s0 > 0) mlp_unit_acquire(P.sched, kTcEpiWarps);
       const float* x0src = (s0 == 0) ? P.x_in : P.x_out;
+      const long long row0 = (s0 == 0 && P.row_index && rv) ? P.row_index[grow] : grow;
       float x[kTcCols];
 #pragma unroll
       for (int i = 0; i < kTcCols; ++i) {
         const int col = col_base + i;
-        x[i] = (rv && col < P.d) ? x0src[grow * P.d + col] : 0.0f;
+        x[i] = (rv && col < P.d) ? x0src[row0 * P.d + col] : 0.0f;
       }
       store_a_cols(smem, row, col_base, x, with_lo);
       signal_cols(smem, first_chunk, lane);
@@ -389,6 +392,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
 #pragma unroll
         for (int i = 0; i < kTcCols; ++i)
           if (col_base + i < P.d) P.x_out[grow * P.d + col_base + i] = x[i];
+        if (P.x_out2 && s1 == P.n_steps) {
+#pragma unroll
+          for (int i = 0; i < kTcCols; ++i)
+            if (col_base + i < P.d) P.x_out2[grow * P.d + col_base + i] = x[i];
+        }
       }
       if (s1 < P.n_steps) mlp_unit_release(P.sched);  // the rest of this tile's burst runs on the next CTA
     }
@@ -444,6 +452,8 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     else { for (int i = 0; i < chunk; ++i) fill_step(tab, i, c.hs[done + i], c.nss[done + i]); tab.mask = ~0; }
     P.x_in = src;
     P.x_out = c.x_out;
+    P.row_index = (done == 0) ? c.row_index : nullptr;
+    P.x_out2 = (done + chunk == c.n_steps) ? c.x_out2 : nullptr;
     P.n_steps = chunk;
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;

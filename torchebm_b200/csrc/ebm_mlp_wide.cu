@@ -78,6 +78,8 @@ struct WdParams {
   float* x_out;
   const float* noise;
   float* traj;
+  const long long* row_index;  // persistent-CD: source row of chain i in x_in (first launch of a burst only), or NULL
+  float* x_out2;               // persistent-CD: second destination of the burst's final state (last launch only), or NULL
   long long n;
   int n_steps, thin, n_kept, step_base, has_clamp;   // step_base: steps of this burst done by earlier launches
   float clamp_lo, clamp_hi;
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     uint32_t xcnt = 0;  // running count of published state chunks: buffer xcnt & 1, use (xcnt >> 1) of that buffer
     const bool with_lo = P.passes == 3;
     // widest aligned access every pointer of this launch allows
-    const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj;
+    const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj | (uintptr_t)P.x_out2;
     const int vec = (P.d % 8 == 0 && (ptr_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (ptr_bits & 15) == 0) ? 1 : 0);
     const long long numel = P.n * P.d;
     uint32_t acc_par = 0, g_par = 0;  // g_par: bit b = parity of g_full[b]
@@ -462,11 +464,14 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       // a unit that starts mid-burst continues the chain another CTA left in x_out
       if (s0 > 0) mlp_unit_acquire(P.sched, kWdEpiWarps);
       const float* x0src = (s0 == 0) ? P.x_in : P.x_out;
+      // row of the launch's input that holds this chain (replay-buffer gather fused into the first load)
+      const long long srow = (P.row_index && rv) ? P.row_index[grow] : grow;
+      const long long row0 = (s0 == 0) ? srow : grow;
       // prologue: publish the unit's initial state chunk by chunk
       for (int c = 0; c < NC; ++c) {
         const int col0 = c * kWdChunk + 16 * cg;
         float v[16];
-        wd_load_x16(x0src, grow, col0, P.d, rv, vec, v);
+        wd_load_x16(x0src, row0, col0, P.d, rv, vec, v);
         const uint32_t xb = xcnt & 1;
         mbar_wait(xa_empty + 8 * xb, ((xcnt >> 1) & 1) ^ 1);
         ++xcnt;
@@ -483,6 +488,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
         const float* xsrc = (k == 0) ? P.x_in : P.x_out;
+        const long long xrow = (k == 0) ? srow : grow;
+        const bool final_step = P.x_out2 && (k == K - 1);
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM [256, 384)
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
         tcgen05_fence_after();
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           // the state chunk is requested first (an L2 hit from the previous step's store); the noise draw below
           // covers its latency
           float xc[16];
-          if (active) wd_load_x16(xsrc, grow, col0, P.d, rv, vec, xc);
+          if (active) wd_load_x16(xsrc, xrow, col0, P.d, rv, vec, xc);
           float eps[16];
           if (active) {
             const long long li0 = grow * P.d + col0;
@@ -594,6 +601,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           wd_publish(xa_full + 8 * xb);
           if (active) {
             wd_store_x16(P.x_out, grow * P.d, col0, P.d, rv, vec, xc);
+            if (final_step) wd_store_x16(P.x_out2, grow * P.d, col0, P.d, rv, vec, xc);
             if (keep_now) wd_store_x16(P.traj, (grow * P.n_kept + (kept - 1)) * P.d, col0, P.d, rv, vec, xc);
           }
         }
@@ -880,6 +888,8 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     else { for (int i = 0; i < chunk; ++i) fill_step(tab, i, c.hs[done + i], c.nss[done + i]); tab.mask = ~0; }
     P.x_in = src;
     P.x_out = c.x_out;
+    P.row_index = (done == 0) ? c.row_index : nullptr;
+    P.x_out2 = (done + chunk == c.n_steps) ? c.x_out2 : nullptr;
     P.n_steps = chunk;
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;

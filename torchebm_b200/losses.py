@@ -76,16 +76,7 @@ class BaseContrastiveDivergence(TorchEBMModule):
             self.initialize_buffer(tuple(x.shape[1:]), generator=generator)
             if not self.buffer_initialized:
                 raise RuntimeError("Buffer initialization failed.")
-        if self.buffer_size < batch_size:
-            warnings.warn(
-                f"Buffer size ({self.buffer_size}) is smaller than batch size ({batch_size}). Sampling with replacement.",
-                UserWarning)
-            indices = torch.randint(0, self.buffer_size, (batch_size,), device=self.device, generator=generator)
-        else:
-            stride = self.buffer_size // batch_size
-            base = torch.arange(0, batch_size, device=self.device) * stride
-            offset = torch.randint(0, stride, (batch_size,), device=self.device, generator=generator)
-            indices = (base + offset) % self.buffer_size
+        indices = self._draw_start_indices(batch_size, generator)
         noise_rows = noise = None
         if self.new_sample_ratio > 0.0:
             n_new = max(1, int(batch_size * self.new_sample_ratio))
@@ -94,6 +85,53 @@ class BaseContrastiveDivergence(TorchEBMModule):
         if self.replay_buffer.is_cuda:
             return ops.pcd_gather(self.replay_buffer, indices, noise_rows, noise)
         raise RuntimeError("the persistent-CD buffer must live on a CUDA device: torchebm_b200 has no CPU path")
+
+    def _draw_start_indices(self, batch_size: int, generator: Optional[torch.Generator]) -> torch.Tensor:
+        """base_loss.py:293-312: stratified start rows (uniform with replacement when the buffer is the smaller)."""
+        if self.buffer_size < batch_size:
+            warnings.warn(
+                f"Buffer size ({self.buffer_size}) is smaller than batch size ({batch_size}). Sampling with replacement.",
+                UserWarning)
+            return torch.randint(0, self.buffer_size, (batch_size,), device=self.device, generator=generator)
+        stride = self.buffer_size // batch_size
+        base = torch.arange(0, batch_size, device=self.device) * stride
+        offset = torch.randint(0, stride, (batch_size,), device=self.device, generator=generator)
+        return (base + offset) % self.buffer_size
+
+    def sample_negatives(self, x: torch.Tensor, model_kwargs: Optional[dict] = None,
+                         generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """The sampling half of `ContrastiveDivergence.forward` (contrastive_divergence.py:127-139): start points,
+        `k_steps` of the sampler, buffer write-back.  Same draws from `generator`, same buffer and pointer state as
+        `get_start_points` -> `sampler.sample` -> `update_buffer`; when the sampler offers `sample_from_buffer` and
+        nothing stands in the way (2-D state, no exploration noise, no conditioning) the three steps are one library
+        call that reads the start rows straight from the replay buffer and writes the final state straight back."""
+        fused = getattr(self.sampler, "sample_from_buffer", None)
+        if (self.persistent and fused is not None and not model_kwargs and self.new_sample_ratio <= 0.0 and x.ndim == 2):
+            x = x.to(device=self.device, dtype=self.dtype)
+            if not self.buffer_initialized:
+                self.initialize_buffer(tuple(x.shape[1:]), generator=generator)
+                if not self.buffer_initialized:
+                    raise RuntimeError("Buffer initialization failed.")
+            if self.replay_buffer.is_cuda and self.replay_buffer.is_contiguous():
+                indices = self._draw_start_indices(x.shape[0], generator)
+                res = fused(self.replay_buffer, indices, self._buffer_ptr_int, self.k_steps, generator=generator)
+                if res is not None:
+                    pred, new_ptr = res
+                    self._buffer_ptr_int = new_ptr
+                    self.buffer_ptr.fill_(new_ptr)
+                    return pred
+                # nothing was consumed beyond the index draw: continue with the gathered start points
+                start_points = ops.pcd_gather(self.replay_buffer, indices)
+                pred = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs, generator=generator)
+                with torch.no_grad():
+                    self.update_buffer(pred)
+                return pred
+        start_points = self.get_start_points(x, generator=generator)
+        pred = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs, generator=generator)
+        if self.persistent:
+            with torch.no_grad():
+                self.update_buffer(pred)
+        return pred
 
     # base_loss.py:390-426
     def update_buffer(self, samples: torch.Tensor) -> None:
@@ -145,12 +183,7 @@ class ContrastiveDivergence(BaseContrastiveDivergence):
     def forward(self, x: torch.Tensor, *args, model_kwargs: Optional[dict] = None,
                 generator: Optional[torch.Generator] = None, **kwargs):
         model_kwargs = self._prepare_model_kwargs(model_kwargs)
-        start_points = self.get_start_points(x, generator=generator)
-        pred_samples = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs,
-                                           generator=generator)
-        if self.persistent:
-            with torch.no_grad():
-                self.update_buffer(pred_samples)
+        pred_samples = self.sample_negatives(x, model_kwargs=model_kwargs, generator=generator)
         kwargs.setdefault("energy_reg_weight", self.energy_reg_weight)
         kwargs.setdefault("add_noise_to_real", self.add_noise_to_real)
         kwargs.setdefault("noise_scale", self.noise_scale)

@@ -192,6 +192,38 @@ def pcd_scatter(buffer: torch.Tensor, ptr: int, samples: torch.Tensor) -> int:
     return int(new_ptr.value)
 
 
+def pcd_langevin_fused(desc: EnergyDescriptor) -> bool:
+    return bool(_lib.load().ebm_pcd_langevin_fused(C.byref(desc.c)))
+
+
+def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: torch.Tensor, ptr: int, n_steps: int,
+                       step_sizes: Sequence[float], noise_scales: Sequence[float], *,
+                       clamp: Optional[Tuple[float, float]] = None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0,
+                       offset: int = 0) -> Tuple[torch.Tensor, int]:
+    """Start points `buffer[idx]` -> K-step burst -> FIFO write-back into `buffer` (in place).  Returns the negatives
+    and the new FIFO pointer (host int, no sync)."""
+    if not buffer.is_contiguous() or buffer.ndim != 2:
+        raise ValueError("replay buffer must be a contiguous [S, D] tensor")
+    buffer = _req(buffer, "buffer")
+    if idx.dtype != torch.int64 or not idx.is_cuda:
+        raise TypeError("idx must be a CUDA int64 tensor")
+    idx = idx.contiguous()
+    n = idx.shape[0]
+    out = torch.empty((n, buffer.shape[1]), dtype=torch.float32, device=buffer.device)
+    scratch = None if pcd_langevin_fused(desc) else torch.empty_like(out)
+    assert len(step_sizes) == len(noise_scales) and len(step_sizes) in (1, n_steps)
+    hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
+    cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
+    new_ptr = C.c_int64(0)
+    with torch.cuda.device(buffer.device):
+        rc = _lib.load().ebm_pcd_langevin_burst_f32(
+            C.byref(desc.c), buffer.data_ptr(), buffer.shape[0], idx.data_ptr(), int(ptr), out.data_ptr(), _ptr(scratch), n,
+            int(n_steps), hs, ns, len(step_sizes), cl, int(rng_mode), int(seed), int(offset), C.byref(new_ptr),
+            _stream(buffer.device))
+    _lib.check(rc, "ebm_pcd_langevin_burst_f32")
+    return out, int(new_ptr.value)
+
+
 def rng_fill(numel: int, device, rng_mode: int, kind: int, seed: int, offset: int) -> torch.Tensor:
     out = torch.empty(numel, dtype=torch.float32, device=device)
     with torch.cuda.device(out.device):

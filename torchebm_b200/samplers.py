@@ -177,6 +177,31 @@ class LangevinDynamics(BaseSampler):
         out = traj if return_trajectory else cur
         return out, diag
 
+    @torch.no_grad()
+    def sample_from_buffer(self, buffer: torch.Tensor, indices: torch.Tensor, ptr: int, n_steps: int, *,
+                           reset_schedulers: bool = True, generator: Optional[torch.Generator] = None):
+        """Persistent-CD negatives in one library call: start points `buffer[indices]`, `n_steps` Langevin steps,
+        FIFO write-back into `buffer` at `ptr` (get_start_points + sample + update_buffer of
+        core/base_loss.py:266-337,390-426 and losses/contrastive_divergence.py:127-139, without exploration noise).
+        Same scheduler and generator semantics as `sample(x=buffer[indices], n_steps=n_steps, generator=generator)`.
+        Returns `(negatives, new_ptr)`, or None when this sampler / energy has no library kernel for it (the caller
+        then takes the three-call path)."""
+        if type(self.integrator) is not EulerMaruyamaIntegrator or buffer.ndim != 2 or not buffer.is_cuda:
+            return None
+        self._require_cuda_fp32()
+        desc = energy_descriptor(self.model, buffer.shape[1], buffer.device)
+        if desc is None or n_steps <= 0:
+            return None
+        if reset_schedulers:
+            self.reset_schedulers()
+        gen, seed, offset = self._rng_state(generator)
+        rng_mode = _lib.RNG_MODES[self.rng]
+        vals, _ = self._advance_schedules(("step_size", "noise_scale"), n_steps)
+        out, new_ptr = ops.pcd_langevin_burst(desc, buffer, indices, ptr, n_steps, vals["step_size"], vals["noise_scale"],
+                                              clamp=self.clamp, rng_mode=rng_mode, seed=seed, offset=offset)
+        gen.set_offset(offset + ops.rng_consumed_langevin(self.device, out.numel(), n_steps, rng_mode))
+        return out, new_ptr
+
     def _empty_diag(self, data_shape, n_kept: int = 0):
         return {
             "mean": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
