@@ -427,3 +427,25 @@ def test_full_size_c2_properties():
     g = torch.Generator(DEV).manual_seed(1)
     c = sampler.sample(x=sampler.sample(x=x0, n_steps=200, generator=g), n_steps=300, generator=g)
     assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("n,d", [(20000, 128), (40001, 77), (3000, 16)])
+@pytest.mark.parametrize("rng_name", ["torch", "native"])
+def test_host_buffer_entry_point_equals_device_burst(n, d, rng_name):
+    """ebm_langevin_burst_host_f32 (pinned host in/out; large bursts are pipelined wave by wave over three streams
+    so the PCIe copies run under the kernel) must give exactly the single-launch device burst."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    mode = _lib.RNG_MODES[rng_name]
+    desc = te.energy_descriptor(te.DoubleWellModel(2.0, 1.0), d, torch.device(DEV))
+    x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(4)).clamp_(-3, 3)
+    want = ops.langevin_burst(desc, x0.to(DEV), 9, [0.01], [1.0], rng_mode=mode, seed=77, offset=16)
+    xh = x0.pin_memory()
+    oh = torch.empty_like(xh).pin_memory()
+    scratch = torch.empty(n, d, device=DEV)
+    for _ in range(2):  # second call reuses the cached streams
+        oh.zero_()
+        ops.langevin_burst_host(desc, xh, oh, scratch, 9, 0.01, 1.0, mode, 77, 16)
+        assert torch.equal(oh, want.cpu())
+    assert torch.equal(xh, x0)

@@ -157,6 +157,9 @@ struct LangevinCall {
   // persistent-CD fusion (ebm_pcd_langevin_burst_f32; MLP kernels only, NULL otherwise):
   const long long* row_index;  // chain i starts from row row_index[i] of x_in (the replay buffer)
   float* x_out2;               // the final state is also written here, row i -> row i (FIFO write-back when S == B)
+  // elementwise kernels only: restrict the launch to owning threads [quad_begin, quad_end) of the burst (0, 0 = all);
+  // the host-buffer entry point pipelines copies against such partial launches
+  unsigned long long quad_begin, quad_end;
 };
 
 inline int row_grid(const DeviceInfo& di, long long n, int G, int ctas_per_sm) {

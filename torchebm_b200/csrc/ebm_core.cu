@@ -146,7 +146,14 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     P.k0 = (uint32_t)c.seed ^ kNativeTag0; P.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
     P.ctr_step = 1;
   }
-  const unsigned long long blocks = (P.n_quads + 255) / 256;
+  P.quad_base = 0;
+  P.quad_end = P.n_quads;
+  if (c.quad_end > c.quad_begin) {
+    P.quad_base = c.quad_begin;
+    P.quad_end = c.quad_end < P.n_quads ? c.quad_end : P.n_quads;
+    if (P.quad_base >= P.quad_end) return 0;
+  }
+  const unsigned long long blocks = (P.quad_end - P.quad_base + 255) / 256;
   if (blocks > 0x7fffffffull) { set_error("too many elements"); return EBM_ERR_UNSUPPORTED; }
 
   const bool uniform = c.schedule_len == 1;
@@ -260,6 +267,22 @@ static int langevin_dispatch(const LangevinCall& c) {
 
 int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                              cudaStream_t st);  // ebm_mlp.cu
+
+// three non-blocking streams per device for the host-buffer entry point (module cache, created on first use);
+// NULL when they cannot be created -- the caller then runs the single-stream path
+static cudaStream_t* host_pipe_streams(int device) {
+  static std::mutex mu;
+  static cudaStream_t streams[64][3];
+  static int state[64];  // 0 = not tried, 1 = ready, -1 = failed
+  if (device < 0 || device >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (state[device] == 0) {
+    state[device] = 1;
+    for (int i = 0; i < 3; ++i)
+      if (cudaStreamCreateWithFlags(&streams[device][i], cudaStreamNonBlocking) != cudaSuccess) { state[device] = -1; break; }
+  }
+  return state[device] == 1 ? streams[device] : nullptr;
+}
 size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e);  // ebm_mlp_wide.cu
 
 }  // namespace ebm
@@ -358,7 +381,7 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
   EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
   EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
-                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr};
+                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0};
   return langevin_dispatch(c);
 }
 
@@ -399,7 +422,7 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
   const bool identity = (n == buffer_rows);
   LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream,
-                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr};
+                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr, 0, 0};
   rc = langevin_dispatch(c);
   if (rc) return rc;
   if (identity) {
@@ -416,8 +439,39 @@ int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, 
   if (rc) return rc;
   EBM_CHECK_ARG(x_in_host && x_out_host && scratch_dev && n > 0, "buffers must be non-null and n positive");
   EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "host entry point draws its own noise");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = (size_t)n * e->dim * sizeof(float);
+  // Elementwise energies: the burst is launched one resident wave of owning threads at a time (in both RNG layouts
+  // a wave owns a contiguous block of 4 * wave elements), each wave on one of three internal streams between the
+  // upload of its block and the download of its result, so the PCIe copies of block c+1 / c-1 run under the kernel
+  // of block c.  The Philox addressing is per element, so the result is identical to the single-launch burst.
+  if (e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN) {
+    const int dev = current_device();
+    const DeviceInfo& di = device_info(dev);
+    const unsigned long long numel = (unsigned long long)n * e->dim;
+    const unsigned long long wave = 256ull * di.sm_count * (di.max_threads_per_sm / 256);
+    const bool layout_ok = rng_mode == EBM_RNG_NATIVE || torch_threads(di, (int64_t)numel) == wave;
+    const unsigned long long n_chunks = (numel + 4 * wave - 1) / (4 * wave);
+    cudaStream_t* pipe = layout_ok && n_chunks >= 2 ? host_pipe_streams(dev) : nullptr;
+    if (pipe) {
+      EBM_CUDA(cudaStreamSynchronize(st));
+      for (unsigned long long ck = 0; ck < n_chunks; ++ck) {
+        cudaStream_t s = pipe[ck % 3];
+        const unsigned long long e0 = 4 * wave * ck;
+        const unsigned long long e1 = (e0 + 4 * wave < numel) ? e0 + 4 * wave : numel;
+        EBM_CUDA(cudaMemcpyAsync(scratch_dev + e0, x_in_host + e0, (e1 - e0) * sizeof(float), cudaMemcpyHostToDevice, s));
+        LangevinCall c{e, scratch_dev, scratch_dev, n, n_steps, &step_size, &noise_scale, 1, nullptr, rng_mode, seed, offset,
+                       nullptr, nullptr, 1, s, nullptr, nullptr, wave * ck, wave * (ck + 1)};
+        rc = langevin_dispatch(c);
+        if (rc) return rc;
+        EBM_CUDA(cudaMemcpyAsync(x_out_host + e0, scratch_dev + e0, (e1 - e0) * sizeof(float), cudaMemcpyDeviceToHost, s));
+      }
+      for (int i = 0; i < 3; ++i) EBM_CUDA(cudaStreamSynchronize(pipe[i]));
+      return 0;
+    }
+  }
   EBM_CUDA(cudaMemcpyAsync(scratch_dev, x_in_host, bytes, cudaMemcpyHostToDevice, st));
   rc = ebm_langevin_burst_f32(e, scratch_dev, scratch_dev, n, n_steps, &step_size, &noise_scale, 1, nullptr, rng_mode,
                               seed, offset, nullptr, nullptr, 1, stream);

@@ -43,14 +43,16 @@ struct LangevinElemParams {
   unsigned long long ctr_step;  // TORCH: inc/4 per step ; NATIVE: 1 per step
   unsigned long long T;         // TORCH layout threads
   unsigned long long n_quads;   // number of owning threads
+  unsigned long long quad_base; // first owning thread of this launch (host-pipelined bursts launch quad ranges)
+  unsigned long long quad_end;  // one past the last owning thread of this launch
 };
 
 template <class EnergyT, int RNG, bool TRAJ, bool CLAMP>
 __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constant__ LangevinElemParams P,
                                                             const EnergyT en,
                                                             const __grid_constant__ StepTable tab) {
-  const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= P.n_quads) return;
+  const unsigned long long gid = P.quad_base + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= P.quad_end) return;
 
   long long idx[4];
   uint32_t c2w, c3w;             // fixed counter words
