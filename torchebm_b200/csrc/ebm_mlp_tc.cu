@@ -266,6 +266,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     const bool with_lo = P.passes == 3;
     const long long numel = P.n * P.d;
     const bool quad_rng = (P.d % 4 == 0);
+    // NATIVE stream: the step's noise is drawn in four 8-column parts, one in front of each wait for a product, and
+    // parked in TMEM columns [384, 512) until the update epilogue -- the draw costs a quarter of the epilogue's
+    // instructions and depends on nothing, so it fills the time the tensor pipe needs to finish each product
+    const bool bubble_rng = (P.rng.mode == 2) && quad_rng;
     uint32_t parity = 0;
 
     for (int tile = units->t_last; tile >= units->t_first; --tile) {
@@ -289,10 +293,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
       rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode;
       rs.ctr_base = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
 
+      auto draw_part = [&](int part) {
+        if (!bubble_rng) return;
+        float e8[8];
+        const uint64_t q0 = (uint64_t)(grow * P.d + col_base + 8 * part) >> 2;
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const uint64_t q = q0 + q4;
+          const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base, (uint32_t)(rs.ctr_base >> 32),
+                                        rs.k0, rs.k1);
+          const float4 nn = normal4_fast(w);
+          e8[4 * q4] = nn.x; e8[4 * q4 + 1] = nn.y; e8[4 * q4 + 2] = nn.z; e8[4 * q4 + 3] = nn.w;
+        }
+        tmem_st8(lane_addr + 384 + 8 * part, e8);
+      };
+
       for (int k = s0; k < s1; ++k) {
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM columns [256, 384)
+        draw_part(0);
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
 #pragma unroll
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
           signal_one(smem, first_chunk + blk, lane);
         }
         // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
+        draw_part(1);
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
 #pragma unroll
@@ -324,6 +345,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
           signal_one(smem, first_chunk + blk, lane);
         }
         // E3: t -> delta1 = t * act'(z1) (A of GEMM4)
+        draw_part(2);
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
         tmem_st_wait();
@@ -339,8 +361,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
           signal_one(smem, first_chunk + blk, lane);
         }
         // E4: g -> Langevin update of x; the new x is the A operand of the next step's GEMM1
+        draw_part(3);
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
+        if (bubble_rng) tmem_st_wait();
         const bool last = (k == s1 - 1);
         bool keep_now = false;
         if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
@@ -349,15 +373,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
           float g[16], eps[16];
           const int c0 = col_base + 16 * blk;
           const long long li0 = grow * P.d + c0;
-          if (P.rng.mode == 2 && quad_rng) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
-              const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base,
-                                            (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
-              const float4 nn = normal4_fast(w);
-              eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
-            }
+          if (bubble_rng) {
+            tmem_ld16(lane_addr + 384 + 16 * blk, eps);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
