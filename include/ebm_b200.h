@@ -76,7 +76,7 @@ typedef struct EbmEnergyDesc {
    *   MoG     : buf[0] = means[K,D], buf[1] = sigmas[K], buf[2] = weights[K]
    *   MLP     : buf[0] = W1[H1,D], buf[1] = b1[H1], buf[2] = W2[H2,H1], buf[3] = b2[H2],
    *             buf[4] = w3[H2], buf[5] = b3[1]            (torch [out,in] layout);
-   *             buf[6] = scratch workspace of ebm_mlp_workspace_bytes() bytes, 128-byte aligned, used by the
+   *             buf[6] = scratch workspace of ebm_workspace_bytes() bytes, 128-byte aligned, used by the
    *             Langevin burst: hand-over flags of the balanced (tile, step-range) work split and, when D > 128,
    *             the per-call bf16 hi/lo re-split of the weights.  Required when D > 128; optional (NULL = whole
    *             tiles per SM, no balancing) when D <= 128.  One workspace must not be shared by bursts running
@@ -94,7 +94,7 @@ int64_t ebm_torch_rng_threads(int device, int64_t numel);
 int64_t ebm_torch_rng_offset_increment(int device, int64_t numel);
 
 /* Bytes of device scratch the Langevin burst needs in e->buf[6] (0 when the energy needs none). */
-int64_t ebm_mlp_workspace_bytes(const EbmEnergyDesc* e);
+int64_t ebm_workspace_bytes(const EbmEnergyDesc* e);
 
 /* E(x) -> energy[n]; replaces `model(x)` (BaseModel.forward, base_model.py:49-60). */
 int ebm_energy_f32(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, void* stream);

@@ -63,7 +63,7 @@ PROTOTYPES = {
     "ebm_device_sm_count": (C.c_int, [C.c_int]),
     "ebm_torch_rng_threads": (_I64, [C.c_int, _I64]),
     "ebm_torch_rng_offset_increment": (_I64, [C.c_int, _I64]),
-    "ebm_mlp_workspace_bytes": (_I64, [_DESC]),
+    "ebm_workspace_bytes": (_I64, [_DESC]),
     "ebm_energy_f32": (C.c_int, [_DESC, _P, _I64, _P, _P]),
     "ebm_gradient_f32": (C.c_int, [_DESC, _P, _I64, _P, _P]),
     "ebm_euler_maruyama_step_f32": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _F64, _P]),

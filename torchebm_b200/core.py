@@ -507,7 +507,7 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         d.precision = _lib.MLP_PRECISIONS[precision]
         for i, t in enumerate(ts):
             d.buf[i] = t.data_ptr()
-        ws_bytes = int(_lib.load().ebm_mlp_workspace_bytes(C.byref(d)))
+        ws_bytes = int(_lib.load().ebm_workspace_bytes(C.byref(d)))
         if ws_bytes > 0 and torch.device(device).type == "cuda":  # hand-over flags + (wide states) the bf16 weight re-split
             ws = _mlp_workspace(device, ws_bytes)
             d.buf[6] = ws.data_ptr()

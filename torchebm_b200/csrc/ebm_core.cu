@@ -315,7 +315,7 @@ int ebm_rng_fill_f32(float* out, int64_t numel, int32_t rng_mode, int32_t kind, 
   return launch_status("rng_fill_kernel");
 }
 
-int64_t ebm_mlp_workspace_bytes(const EbmEnergyDesc* e) {
+int64_t ebm_workspace_bytes(const EbmEnergyDesc* e) {
   if (!e || e->kind != EBM_ENERGY_MLP) return 0;
   if (e->dim <= 128) return kMlpFlagBytes;  // hand-over flags of the balanced tile-step split (optional: buf[6] may be NULL)
   return (int64_t)mlp_wide_workspace_bytes(e);

@@ -837,7 +837,7 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     return EBM_ERR_UNSUPPORTED;
   }
   if (!e->buf[6]) {
-    set_error("MLP energies with dim > 128 need a device workspace of ebm_mlp_workspace_bytes() bytes in buf[6]");
+    set_error("MLP energies with dim > 128 need a device workspace of ebm_workspace_bytes() bytes in buf[6]");
     return EBM_ERR_INVALID;
   }
   if (((uintptr_t)e->buf[6] & 127) != 0) { set_error("MLP workspace must be 128-byte aligned"); return EBM_ERR_INVALID; }
