@@ -224,11 +224,36 @@ def run_ours(args):
         x_local = x_full[lo:hi].to(dev)
     out_local = torch.empty_like(x_local)
     gathered = torch.empty(n_total, d, device=dev) if world > 1 else None
+    # C2 at N > 1: the burst kernel stores its shard straight into every rank's gathered tensor (symmetric memory, NVLink
+    # peer stores) and a device-side barrier replaces the NCCL all-gather; NCCL stays the fallback if peer mapping fails
+    peer = None
+    if world > 1 and args.workload == "c2" and not args.nccl_gather:
+        ok = torch.ones(1, device=dev)
+        try:
+            from torchebm_b200.distributed import PeerGatherBuffer
+            peer = PeerGatherBuffer(n_total, d, dev)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer-mapped gather unavailable ({exc!r}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            peer = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    if peer is not None:
+        inc2 = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
+
+        def step(x, out, it, kev=None):  # noqa: F811  (same burst, gather fused into its final store)
+            if kev: kev[0].record()
+            ops.langevin_burst_gather(desc, x, k, [0.01], [1.0], peer.ptrs, rank * n_local, rng_mode=_lib.RNG_TORCH,
+                                      seed=1234, offset=it * inc2, out=out)
+            if kev: kev[1].record()
+            peer.barrier()
+            return 1, out
 
     def one_step(it):
         n, res = step(x_local, out_local, it)
-        if world > 1:
+        if world > 1 and peer is None:
             gather_chains(res, out=gathered)
         return n
 
@@ -253,7 +278,7 @@ def run_ours(args):
             starts[it].record()
             n_l, res = step(x_local, out_local, args.warmup + it, (kstarts[it], kends[it]))
             launches += n_l
-            if world > 1:
+            if world > 1 and peer is None:
                 gather_chains(res, out=gathered)
             ends[it].record()
         barrier()
@@ -320,7 +345,10 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc_text,
                    "rng": ("native-layout" if args.workload.startswith("mlp128") or args.workload in ("c3", "c5") else "torch-layout") + " Philox4x32-10 drawn in-kernel",
-                   "chains_per_gpu": n_local, "collective": "all_gather of [N/W, D] shards at burst end" if world > 1 else "none",
+                   "chains_per_gpu": n_local, "collective": ("none" if world == 1 else
+                                  "burst-end gather fused into the kernel's final store (NVLink peer stores into symmetric "
+                                  "memory) + device-side barrier" if peer is not None else
+                                  "NCCL all_gather of [N/W, D] shards at burst end"),
                    "l2": "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events"},
         "e2e": e2e,
         "gpu_launches": launches,
@@ -446,6 +474,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-k", type=int, default=5, help="Langevin steps per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: use the NCCL all-gather instead of fused peer stores")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

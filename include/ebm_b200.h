@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 4
+#define EBM_ABI_VERSION 5
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -122,6 +122,18 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
                            int32_t schedule_len, const float* clamp_lo_hi_host, int32_t rng_mode,
                            uint64_t seed, uint64_t offset, const float* noise, float* traj, int32_t thin,
                            void* stream);
+
+/* Same burst on one rank of a box whose chains are sharded over `world` GPUs, with the burst-end all-gather (the one
+ * collective of the sharded path) fused into the kernel's final store: besides x_out[n, dim] the final state is written
+ * at rows [row_offset, row_offset + n) of EVERY rank's gathered buffer.  peer_out_host[w] (host array of `world` device
+ * pointers, world <= 16) is rank w's gathered [n_total, dim] buffer as mapped into THIS process (peer / symmetric
+ * memory; the own rank's entry is its local buffer).  Remote stores travel over NVLink from inside the burst kernel
+ * (elementwise energies) or as copy-engine pushes (other energies).  The caller runs a cross-rank barrier on the stream
+ * afterwards, before any rank reads its gathered buffer. */
+int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                                  const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                  const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                  float* const* peer_out_host, int32_t world, int64_t row_offset, void* stream);
 
 /* Same burst with HOST buffers: copies x_in_host -> device scratch, runs the burst, copies the result
  * back into x_out_host and synchronises `stream`.  `scratch_dev` must hold n*dim floats.

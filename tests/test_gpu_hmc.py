@@ -214,3 +214,41 @@ def test_hmc_errors():
     mean, cov = torch.zeros(3), torch.eye(3)
     sg = te.HamiltonianMonteCarlo(te.GaussianModel(mean, cov).to(DEV), step_size=0.1, device=DEV)
     assert sg.sample(n_samples=7, n_steps=2).shape == (7, 3)  # dim inferred from model.mean (hmc.py:209-217)
+
+
+def test_hmc_integrator_level_path_for_mlp_and_custom_energies():
+    """Energies without a fused HMC kernel (MLP energies, arbitrary nn.Modules) go proposal by proposal through the
+    integrator with the reference's draw order; same seed on CUDA => same chains as the oracle (tolerance: the MLP
+    gradient comes from the library's fused kernel instead of autograd)."""
+    import torchebm_b200 as te
+
+    torch.manual_seed(4)
+    d = 12
+    mlp = te.MLPEnergy(dim=d, hidden=(32, 24), activation="tanh", precision="fp32").to(DEV)
+    lin = [l for l in mlp.net if isinstance(l, torch.nn.Linear)]
+    en = E.MLP([l.weight for l in lin], [l.bias for l in lin], "tanh")
+    x0 = torch.randn(500, d, device=DEV)
+    for mass in (None, 2.5, torch.rand(d, device=DEV) + 0.5):
+        s = te.HamiltonianMonteCarlo(mlp, step_size=0.05, n_leapfrog_steps=4, mass=mass, device=DEV)
+        got, diag = s.sample(x=x0, n_steps=6, thin=2, return_trajectory=True, return_diagnostics=True,
+                             generator=torch.Generator(DEV).manual_seed(8))
+        want, wdiag = ohmc.sample(en, x0, 6, 0.05, 4, mass=mass, thin=2, return_trajectory=True, return_diagnostics=True,
+                                  generator=torch.Generator(DEV).manual_seed(8))
+        assert got.shape == (500, 3, d)
+        bad = ((got - want).abs().amax(dim=(1, 2)) > 1e-4).float().mean().item()
+        assert bad < 0.01, bad   # a borderline accept decision may flip on a last-ulp energy difference
+        torch.testing.assert_close(diag["acceptance_rate"], wdiag["acceptance_rate"], atol=0.01, rtol=0)
+
+    class Quartic(torch.nn.Module):  # not a library energy: its own forward + autograd gradient
+        def forward(self, x):
+            return 0.25 * (x ** 4).sum(-1) + 0.5 * (x[:, :-1] * x[:, 1:]).sum(-1)
+
+    class QuarticE(E.Energy):
+        def energy(self, x):
+            return 0.25 * (x ** 4).sum(-1) + 0.5 * (x[:, :-1] * x[:, 1:]).sum(-1)
+
+    s = te.HamiltonianMonteCarlo(Quartic(), step_size=0.05, n_leapfrog_steps=5, device=DEV)
+    got = s.sample(x=x0, n_steps=4, generator=torch.Generator(DEV).manual_seed(9))
+    want = ohmc.sample(QuarticE(), x0, 4, 0.05, 5, generator=torch.Generator(DEV).manual_seed(9))
+    bad = ((got - want).abs().amax(dim=1) > 1e-5).float().mean().item()
+    assert bad < 0.01, bad

@@ -1,0 +1,66 @@
+"""Two-GPU checks of the sharded path (skipped on a one-GPU box): the burst-end gather fused into the burst kernel's
+final store (peer stores into symmetric memory) must equal an NCCL all-gather of the per-rank results."""
+
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, d, k, result_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+    from torchebm_b200.distributed import PeerGatherBuffer, gather_chains, shard_bounds
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        lo, hi = shard_bounds(n_total, rank, world)
+        x_full = torch.randn(n_total, d, generator=torch.Generator().manual_seed(0)).clamp_(-3, 3)
+        x_local = x_full[lo:hi].to(dev)
+        results = {}
+        for name, model in (("doublewell", te.DoubleWellModel(2.0, 1.0)), ("rastrigin", te.RastriginModel(10.0)),
+                            ("gaussian", te.GaussianModel(torch.zeros(d), torch.eye(d)).to(dev))):
+            desc = te.energy_descriptor(model, d, dev)
+            buf = PeerGatherBuffer(n_total, d, dev)
+            buf.tensor.fill_(float("nan"))
+            buf.barrier()
+            for rng_mode in (_lib.RNG_TORCH, _lib.RNG_NATIVE):
+                local = buf.burst(desc, x_local, k, [0.01], [1.0], rng_mode=rng_mode, seed=100 + rank, offset=0)
+                torch.cuda.synchronize()
+                want_local = ops.langevin_burst(desc, x_local, k, [0.01], [1.0], rng_mode=rng_mode, seed=100 + rank, offset=0)
+                want = gather_chains(want_local)
+                results[f"{name}_{rng_mode}"] = bool(torch.equal(local, want_local) and torch.equal(buf.tensor, want))
+                buf.barrier()  # nobody may overwrite a peer's buffer before that peer has compared it
+        torch.save(results, os.path.join(result_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_fused_peer_gather_equals_nccl_all_gather(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.start_processes(_worker, args=(2, port, 2 * 5000, 96, 6, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    for rank in range(2):
+        res = torch.load(os.path.join(str(tmp_path), f"rank{rank}.pt"))
+        assert res and all(res.values()), (rank, res)

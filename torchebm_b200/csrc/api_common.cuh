@@ -160,6 +160,10 @@ struct LangevinCall {
   // elementwise kernels only: restrict the launch to owning threads [quad_begin, quad_end) of the burst (0, 0 = all);
   // the host-buffer entry point pipelines copies against such partial launches
   unsigned long long quad_begin, quad_end;
+  // burst-end gather (ebm_langevin_burst_gather_f32): peer-mapped gathered buffers, this rank's first row in them
+  float* const* peers;
+  int n_peers;
+  long long peer_row_offset;
 };
 
 inline int row_grid(const DeviceInfo& di, long long n, int G, int ctas_per_sm) {

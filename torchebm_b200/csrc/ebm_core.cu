@@ -168,6 +168,12 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     P.x_in = src;
     P.x_out = c.x_out;
     P.n_steps = chunk;
+    P.n_peers = 0;
+    if (c.n_peers > 0 && done + chunk == c.n_steps) {  // the last launch of the burst also feeds the gathered buffers
+      P.n_peers = c.n_peers;
+      P.peer_off = c.peer_row_offset * c.e->dim;
+      for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
+    }
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.ctr_base = c.offset / 4 + (unsigned long long)done * P.ctr_step;
     P.thin_start = c.thin - (done % c.thin);
@@ -381,8 +387,36 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
   EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
   EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
-                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0};
+                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0, nullptr, 0, 0};
   return langevin_dispatch(c);
+}
+
+int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                                  const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                  const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                  float* const* peer_out_host, int32_t world, int64_t row_offset, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x_in && x_out && n > 0, "x_in/x_out must be non-null and n positive");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(step_size_host && noise_scale_host, "schedules must be non-null");
+  EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
+  EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "the gathering burst draws its own noise");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  EBM_CHECK_ARG(peer_out_host && world >= 1 && world <= kMaxPeers, "peer_out_host must hold 1..16 pointers");
+  EBM_CHECK_ARG(row_offset >= 0, "row_offset must be non-negative");
+  for (int w = 0; w < world; ++w) EBM_CHECK_ARG(peer_out_host[w], "null peer pointer");
+  const bool fused = e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN;
+  LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                 rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, nullptr, 0, 0,
+                 fused ? peer_out_host : nullptr, fused ? world : 0, row_offset};
+  rc = langevin_dispatch(c);
+  if (rc || fused) return rc;
+  // energies whose burst kernel has no peer-store epilogue yet: copy-engine pushes of the shard into every buffer
+  const size_t bytes = (size_t)n * e->dim * sizeof(float);
+  for (int w = 0; w < world; ++w)
+    EBM_CUDA(cudaMemcpyAsync(peer_out_host[w] + row_offset * e->dim, x_out, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
 }
 
 int ebm_pcd_langevin_fused(const EbmEnergyDesc* e) {
@@ -422,7 +456,7 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
   const bool identity = (n == buffer_rows);
   LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream,
-                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr, 0, 0};
+                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr, 0, 0, nullptr, 0, 0};
   rc = langevin_dispatch(c);
   if (rc) return rc;
   if (identity) {
@@ -463,7 +497,7 @@ int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, 
         const unsigned long long e1 = (e0 + 4 * wave < numel) ? e0 + 4 * wave : numel;
         EBM_CUDA(cudaMemcpyAsync(scratch_dev + e0, x_in_host + e0, (e1 - e0) * sizeof(float), cudaMemcpyHostToDevice, s));
         LangevinCall c{e, scratch_dev, scratch_dev, n, n_steps, &step_size, &noise_scale, 1, nullptr, rng_mode, seed, offset,
-                       nullptr, nullptr, 1, s, nullptr, nullptr, wave * ck, wave * (ck + 1)};
+                       nullptr, nullptr, 1, s, nullptr, nullptr, wave * ck, wave * (ck + 1), nullptr, 0, 0};
         rc = langevin_dispatch(c);
         if (rc) return rc;
         EBM_CUDA(cudaMemcpyAsync(x_out_host + e0, scratch_dev + e0, (e1 - e0) * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -15,6 +15,7 @@
 namespace ebm {
 
 constexpr int kSchedChunk = 64;
+constexpr int kMaxPeers = 16;
 
 struct StepTable {           // per-step coefficients, fp32 as torch rounds the Python doubles
   float h[kSchedChunk];      // step_size
@@ -45,6 +46,11 @@ struct LangevinElemParams {
   unsigned long long n_quads;   // number of owning threads
   unsigned long long quad_base; // first owning thread of this launch (host-pipelined bursts launch quad ranges)
   unsigned long long quad_end;  // one past the last owning thread of this launch
+  // burst-end gather fused into the final store: the state is also written at element offset peer_off of every
+  // peer-mapped gathered buffer (NVLink stores; ebm_langevin_burst_gather_f32)
+  int n_peers;
+  long long peer_off;
+  float* peers[kMaxPeers];
 };
 
 template <class EnergyT, int RNG, bool TRAJ, bool CLAMP>
@@ -144,6 +150,16 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (ok[i]) P.x_out[idx[i]] = x[i];
+  }
+  for (int w = 0; w < P.n_peers; ++w) {  // one store per rank of the box, over NVLink for the remote ones
+    float* dst = P.peers[w] + P.peer_off;
+    if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      *reinterpret_cast<float4*>(dst + idx[0]) = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ok[i]) dst[idx[i]] = x[i];
+    }
   }
 }
 

@@ -83,3 +83,43 @@ def rank_generator(base_seed: int, device, group=None) -> torch.Generator:
     g = torch.Generator(device=device)
     g.manual_seed(int(base_seed) + get_rank(group))
     return g
+
+
+class PeerGatherBuffer:
+    """The gathered `[n_total, dim]` chain tensor of a sharded burst, allocated in symmetric (peer-mapped) memory so that
+    every rank's burst kernel can store its shard straight into every other rank's copy over NVLink
+    (`ops.langevin_burst_gather`): the burst-end all-gather without a separate collective launch.
+
+    Collective: every rank of `group` must construct it (rendezvous) with the same shape.  `barrier()` is a device-side
+    cross-rank barrier on the current stream: call it after the burst before reading `tensor`, and again before the
+    next burst overwrites the buffers if a reader may still be using them."""
+
+    def __init__(self, n_total: int, dim: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not is_distributed():
+            raise RuntimeError("PeerGatherBuffer needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.tensor = symm_mem.empty((n_total, dim), dtype=torch.float32, device=torch.device(device))
+        self.handle = symm_mem.rendezvous(self.tensor, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.rank = int(self.handle.rank)
+        self.world = int(self.handle.world_size)
+        if n_total % self.world != 0:
+            raise ValueError(f"n_total ({n_total}) must be divisible by the world size ({self.world})")
+        self.rows_per_rank = n_total // self.world
+
+    def barrier(self) -> None:
+        self.handle.barrier(channel=0)
+
+    def burst(self, desc, x_local: torch.Tensor, n_steps: int, step_sizes, noise_scales, **kw) -> torch.Tensor:
+        """Run this rank's burst and push the result into every rank's gathered tensor; returns the local result.
+        The gathered tensor is complete on all ranks after the barrier this method issues."""
+        from . import ops
+
+        if x_local.shape[0] != self.rows_per_rank:
+            raise ValueError("every rank must hold n_total / world chains")
+        out = ops.langevin_burst_gather(desc, x_local, n_steps, step_sizes, noise_scales, self.ptrs,
+                                        self.rank * self.rows_per_rank, **kw)
+        self.barrier()
+        return out

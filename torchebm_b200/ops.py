@@ -111,6 +111,27 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
     return out
 
 
+def langevin_burst_gather(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_sizes: Sequence[float],
+                          noise_scales: Sequence[float], peer_ptrs: Sequence[int], row_offset: int, *,
+                          clamp: Optional[Tuple[float, float]] = None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0,
+                          offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K-step burst whose final state also lands at rows [row_offset, row_offset + n) of every rank's gathered buffer
+    (`peer_ptrs[w]` = rank w's buffer as mapped into this process).  A cross-rank barrier must follow on the stream."""
+    x = _req(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    assert len(step_sizes) == len(noise_scales) and len(step_sizes) in (1, n_steps)
+    hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
+    cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
+    peers = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(x.device):
+        rc = _lib.load().ebm_langevin_burst_gather_f32(
+            C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs, ns, len(step_sizes), cl,
+            int(rng_mode), int(seed), int(offset), peers, len(peer_ptrs), int(row_offset), _stream(x.device))
+    _lib.check(rc, "ebm_langevin_burst_gather_f32")
+    return out
+
+
 def leapfrog(desc: EnergyDescriptor, x: torch.Tensor, p: torch.Tensor, step_size: float, n_steps: int,
              mass=None, safe: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     x, p = _req(x, "x"), _req(p, "p")

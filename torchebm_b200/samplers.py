@@ -284,9 +284,9 @@ class HamiltonianMonteCarlo(BaseSampler):
         n_kept = n_steps // thin
         desc = self._descriptor(x, model_kwargs) if type(self.integrator) is LeapfrogIntegrator else None
         if desc is None or desc.kind == "mlp":
-            raise _lib.EbmUnsupported(
-                f"HamiltonianMonteCarlo has fused kernels for the analytic energies only; "
-                f"{type(self.model).__name__} is not one of them")
+            # no fused HMC kernel for this energy (custom models, MLP energies, conditioning, custom symplectic
+            # integrators): the integrator-level path, hmc.py:244-312 step for step
+            return self._sample_opaque(x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator)
         x = x.contiguous()
         rng_mode = _lib.RNG_MODES[self.rng]
         traj = torch.empty((n, n_kept, d), dtype=self.dtype, device=self.device) if return_trajectory else None
@@ -333,3 +333,52 @@ class HamiltonianMonteCarlo(BaseSampler):
         gen.set_offset(offset)
         out = traj if return_trajectory else cur
         return out, diag
+
+    def _kinetic(self, p: torch.Tensor) -> torch.Tensor:
+        """hmc.py:136-159."""
+        if self.mass is None:
+            return 0.5 * torch.sum(p.square(), dim=-1)
+        if isinstance(self.mass, float):
+            return 0.5 * torch.sum(p.square(), dim=-1) / self.mass
+        return 0.5 * torch.sum(p.square() / self.mass.view((1,) * (p.ndim - 1) + (-1,)), dim=-1)
+
+    def _sample_opaque(self, x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator):
+        """Energies with no fused HMC kernel: their own energy / gradient (the library's MLP kernels when the model is
+        an `MLPEnergy`, autograd otherwise) driven through the integrator, proposal by proposal, in the reference's
+        order of operations and draws (hmc.py:244-312: `normal_` for the momentum, `rand(N)` for the accept test)."""
+        n, d = x.shape
+        n_kept = n_steps // thin
+        traj = torch.empty((n, n_kept, d), dtype=self.dtype, device=self.device) if return_trajectory else None
+        diag = None
+        if return_diagnostics:
+            diag = {k: torch.empty(n_kept, d, dtype=self.dtype, device=self.device) for k in ("mean", "var")}
+            diag["energy"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
+            diag["acceptance_rate"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
+        drift = lambda x_, t_: -self._model_gradient(x_, model_kwargs)
+        keep = 0
+        for i in range(n_steps):
+            p = torch.empty_like(x).normal_(generator=generator)
+            if self.mass is not None:
+                p = p * (self.mass ** 0.5 if isinstance(self.mass, float) else torch.sqrt(self.mass).view(1, -1))
+            h0 = self._model_energy(x, model_kwargs).clamp(min=-1e10, max=1e10) + self._kinetic(p).clamp(min=0.0, max=1e10)
+            prop = self.integrator.integrate({"x": x, "p": p}, step_size=self.get_scheduled_value("step_size"),
+                                             n_steps=self.n_leapfrog_steps, mass=self.mass, drift=drift, safe=True)
+            xp, pp = prop["x"], prop["p"]
+            h1 = self._model_energy(xp, model_kwargs).clamp(min=-1e10, max=1e10) + self._kinetic(pp).clamp(min=0.0, max=1e10)
+            acc_prob = torch.exp((h0 - h1).clamp(min=-50.0, max=50.0)).clamp(max=1.0)
+            u = torch.rand(n, device=self.device, dtype=self.dtype, generator=generator)
+            accepted = u < acc_prob
+            x = torch.where(accepted.view(-1, 1), xp, x)
+            if (i + 1) % thin == 0:
+                if traj is not None:
+                    traj[:, keep, :] = x
+                if diag is not None:
+                    diag["mean"][keep] = x.mean(dim=0)
+                    diag["var"][keep] = (x.var(dim=0, unbiased=False).clamp_(min=1e-10, max=1e10) if n > 1
+                                         else torch.zeros(d, dtype=self.dtype, device=self.device))
+                    diag["energy"][keep] = self._model_energy(x, model_kwargs).clamp(min=-1e10, max=1e10).mean()
+                    diag["acceptance_rate"][keep] = accepted.to(self.dtype).mean()
+                keep += 1
+            self.step_schedulers()
+        out = traj if return_trajectory else x
+        return (out, diag) if return_diagnostics else out
