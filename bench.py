@@ -179,6 +179,8 @@ def make_workload(name: str, n_local: int, dev):
         torch.manual_seed(0)
         model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev)
         sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=dev, rng="native")
+        if name in WEAK and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            model.sm_margin = 1  # the burst-end gather of burst i runs next to burst i+1: leave it an SM for its barrier kernel
         cd = te.ContrastiveDivergence(model, sampler, k_steps=k, persistent=True, buffer_size=n_local, init_steps=0,
                                       new_sample_ratio=0.0, device=dev)
         gen = torch.Generator(dev).manual_seed(1234)
@@ -223,11 +225,11 @@ def run_ours(args):
         x_full = torch.randn(n_total, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
         x_local = x_full[lo:hi].to(dev)
     out_local = torch.empty_like(x_local)
-    gathered = torch.empty(n_total, d, device=dev) if world > 1 else None
+    gathered = None
     # C2 at N > 1: the burst kernel stores its shard straight into every rank's gathered tensor (symmetric memory, NVLink
     # peer stores) and a device-side barrier replaces the NCCL all-gather; NCCL stays the fallback if peer mapping fails
     peer = None
-    if world > 1 and args.workload == "c2" and not args.nccl_gather:
+    if world > 1 and args.workload in ("c2", "c5") and not args.nccl_gather:
         ok = torch.ones(1, device=dev)
         try:
             from torchebm_b200.distributed import PeerGatherBuffer
@@ -238,9 +240,11 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() == 0:
             peer = None
+    if world > 1 and peer is None:
+        gathered = torch.empty(n_total, d, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    if peer is not None:
+    if peer is not None and args.workload == "c2":
         inc2 = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
 
         def step(x, out, it, kev=None):  # noqa: F811  (same burst, gather fused into its final store)
@@ -251,10 +255,30 @@ def run_ours(args):
             peer.barrier()
             return 1, out
 
+    # C5 (weak scaling, 1.6 GB gathered per GPU at N = 8): the NCCL all-gather of burst i runs on a side stream underneath
+    # burst i+1 (the negatives are a fresh tensor per burst; the loss needs only the local ones, core/base_loss.py:131-134)
+    side = torch.cuda.Stream(device=dev) if (world > 1 and args.workload in WEAK) else None
+
+    fused_gather = peer is not None and args.workload == "c2"   # the burst kernel itself stores into the peers
+
+    def gather(res):
+        if side is None:
+            gather_chains(res, out=gathered)
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        res.record_stream(side)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            if peer is not None:
+                peer.push(res)      # peer-to-peer DMA copies + device barrier: no SM taken from the running burst
+            else:
+                gather_chains(res, out=gathered)
+
     def one_step(it):
         n, res = step(x_local, out_local, it)
-        if world > 1 and peer is None:
-            gather_chains(res, out=gathered)
+        if world > 1 and not fused_gather:
+            gather(res)
         return n
 
     def barrier():
@@ -274,15 +298,22 @@ def run_ours(args):
     with ClockSampler(local) as clocks:
         barrier()
         for it in range(args.steps):
-            flush.zero_()  # evict the state from L2 between timed iterations (not timed)
+            if side is None:
+                flush.zero_()  # evict the state from L2 between timed iterations (not timed)
             starts[it].record()
             n_l, res = step(x_local, out_local, args.warmup + it, (kstarts[it], kends[it]))
             launches += n_l
-            if world > 1 and peer is None:
-                gather_chains(res, out=gathered)
+            if world > 1 and not fused_gather:
+                gather(res)
             ends[it].record()
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)  # the last gather ends inside the timed region
+            tail = torch.cuda.Event(enable_timing=True)
+            tail.record()
         barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    if side is not None:  # overlapped collectives: time the whole region, first burst start to last gather end
+        total_ms = starts[0].elapsed_time(tail)
     kernel_ms = sum(s.elapsed_time(e) for s, e in zip(kstarts, kends))
     if world > 1:
         t = torch.tensor([total_ms, kernel_ms], device=dev, dtype=torch.float64)
@@ -347,9 +378,14 @@ def run_ours(args):
                    "rng": ("native-layout" if args.workload.startswith("mlp128") or args.workload in ("c3", "c5") else "torch-layout") + " Philox4x32-10 drawn in-kernel",
                    "chains_per_gpu": n_local, "collective": ("none" if world == 1 else
                                   "burst-end gather fused into the kernel's final store (NVLink peer stores into symmetric "
-                                  "memory) + device-side barrier" if peer is not None else
-                                  "NCCL all_gather of [N/W, D] shards at burst end"),
-                   "l2": "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events"},
+                                  "memory) + device-side barrier" if fused_gather else
+                                  "burst-end gather as peer-to-peer DMA copies into symmetric memory + device-side barrier, on a "
+                                  "side stream under the next burst" if peer is not None else
+                                  "NCCL all_gather of [N/W, D] shards at burst end, on a side stream under the next burst"
+                                  if side is not None else "NCCL all_gather of [N/W, D] shards at burst end"),
+                   "l2": ("no flush: every burst streams a 205 MB state, larger than the 126 MB L2; one CUDA-event window over "
+                          "all steps" if side is not None else
+                          "flushed between timed iterations (256 MiB memset, untimed); per-step CUDA events")},
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clocks.summary(),

@@ -65,7 +65,9 @@ typedef struct EbmEnergyDesc {
   int32_t hidden2;      /* MLP: H2 */
   int32_t activation;   /* MLP: EBM_ACT_* */
   int32_t precision;    /* MLP: EBM_MLP_* (Langevin burst only; energy/gradient evaluation is always FP32) */
-  int32_t reserved;
+  int32_t sm_margin;    /* MLP: SMs the persistent burst kernels leave free (0 = use all).  A burst that runs next to
+                           a collective on another stream needs >= 1: its CTAs fill every SM they get, and a barrier or
+                           copy kernel of the collective would otherwise wait for the whole burst. */
   /* scalar parameters (fp32, already rounded the way torch rounds the Python doubles):
    *   DoubleWell: p[0] = barrier_height, p[1] = b*b
    *   Harmonic  : p[0] = 0.5*k

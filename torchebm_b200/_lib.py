@@ -36,7 +36,7 @@ class EbmEnergyDesc(C.Structure):
         ("hidden2", C.c_int32),
         ("activation", C.c_int32),
         ("precision", C.c_int32),
-        ("reserved", C.c_int32),
+        ("sm_margin", C.c_int32),
         ("p", C.c_float * 4),
         ("buf", C.c_void_p * 8),
     ]

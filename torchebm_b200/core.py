@@ -370,6 +370,8 @@ class MLPEnergy(BaseModel):
         #: arithmetic of the fused Langevin products: "bf16x3" (tensor cores, split operands, ~2e-5 relative),
         #: "fp32" (CUDA cores) or "bf16" (tensor cores, single pass, ~4e-3 relative)
         self.precision = precision
+        #: SMs the persistent burst kernels leave free; set >= 1 when a collective runs next to the bursts on another stream
+        self.sm_margin = 0
         if net is None:
             if dim is None:
                 raise ValueError("dim must be given when net is None")
@@ -505,6 +507,7 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         if l1.in_features > MLP_MAX_WIDTH and precision == "fp32":
             precision = "bf16x3"  # wide states have a tensor-core kernel only (same accuracy class as fp32)
         d.precision = _lib.MLP_PRECISIONS[precision]
+        d.sm_margin = int(getattr(model, "sm_margin", 0))
         for i, t in enumerate(ts):
             d.buf[i] = t.data_ptr()
         ws_bytes = int(_lib.load().ebm_workspace_bytes(C.byref(d)))

@@ -456,7 +456,8 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.rng.ctr_step = 1;
   }
   const long long tiles = (c.n + kTcM - 1) / kTcM;
-  const int grid = (int)(tiles < di.sm_count ? tiles : di.sm_count);
+  const int sms = (e->sm_margin > 0 && e->sm_margin < di.sm_count) ? di.sm_count - e->sm_margin : di.sm_count;
+  const int grid = (int)(tiles < sms ? tiles : sms);
   int* flags = reinterpret_cast<int*>(const_cast<float*>(e->buf[6]));  // NULL: whole tiles per CTA (no balancing)
   const bool uniform = c.schedule_len == 1;
   int done = 0;

@@ -875,7 +875,8 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     if (rc) return rc;
   }
   const long long tiles = (c.n + kWdM - 1) / kWdM;
-  const int grid = (int)(tiles < di.sm_count ? tiles : di.sm_count);
+  const int sms = (e->sm_margin > 0 && e->sm_margin < di.sm_count) ? di.sm_count - e->sm_margin : di.sm_count;
+  const int grid = (int)(tiles < sms ? tiles : sms);
   int* flags = reinterpret_cast<int*>(const_cast<float*>(e->buf[6])) + mlp_wide_weight_bytes(e) / 4;
   const bool uniform = c.schedule_len == 1;
   int done = 0;

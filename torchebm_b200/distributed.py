@@ -112,6 +112,19 @@ class PeerGatherBuffer:
     def barrier(self) -> None:
         self.handle.barrier(channel=0)
 
+    def push(self, x_local: torch.Tensor) -> None:
+        """Copy-engine gather: store this rank's finished shard into every rank's gathered tensor with peer-to-peer
+        DMA copies on the current stream (no SM is used, so it overlaps a burst running on another stream), then the
+        cross-rank barrier.  For bursts whose kernel has no peer-store epilogue (MLP energies)."""
+        if x_local.shape[0] != self.rows_per_rank:
+            raise ValueError("every rank must hold n_total / world chains")
+        lo = self.rank * self.rows_per_rank
+        shape, dtype = tuple(self.tensor.shape), self.tensor.dtype
+        for w in range(self.world):
+            dst = self.tensor if w == self.rank else self.handle.get_buffer(w, shape, dtype)
+            dst[lo:lo + self.rows_per_rank].copy_(x_local, non_blocking=True)
+        self.barrier()
+
     def burst(self, desc, x_local: torch.Tensor, n_steps: int, step_sizes, noise_scales, **kw) -> torch.Tensor:
         """Run this rank's burst and push the result into every rank's gathered tensor; returns the local result.
         The gathered tensor is complete on all ranks after the barrier this method issues."""
