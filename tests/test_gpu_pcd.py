@@ -111,19 +111,54 @@ def test_cd_buffer_warmup_and_full_overwrite():
     assert cd._buffer_ptr_int == 0 and torch.equal(cd.replay_buffer, neg)
 
 
-def test_c3_shape_cd_step_runs_fused():
-    """BASELINE config 3 shape at reduced width (D=128: this build's MLP kernel limit): persistent CD, N=65536, k=20."""
+def test_c3_full_size_cd_step_properties():
+    """BASELINE config 3 at full size: persistent CD, MLP 784-128-128-1, N = 65 536 = buffer_size, k = 20, through the
+    size-independent properties the path offers:
+    * the one-call negatives equal get_start_points -> sample -> update_buffer bit for bit (same seed), the buffer is the
+      negatives and the FIFO pointer wraps to 0;
+    * pure diffusion (an energy with zero weights has zero gradient): x_K - x_0 is N(0, 2 h K sigma^2) per element, which
+      pins the in-kernel noise scale and the update arithmetic at full size;
+    * nearly noise-free chains descend the energy (gradient direction and step sign);
+    * the loss is finite and differentiable."""
     import torchebm_b200 as te
 
+    n, d, k = 65536, 784, 20
     torch.manual_seed(0)
-    model = te.MLPEnergy(dim=128, hidden=128, activation="silu").to(DEV)
-    sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV)
-    cd = te.ContrastiveDivergence(model, sampler, k_steps=20, persistent=True, buffer_size=65536, init_steps=0,
-                                  new_sample_ratio=0.0, device=DEV)
-    x = torch.randn(65536, 128, device=DEV)
-    loss, neg = cd(x, generator=torch.Generator(DEV).manual_seed(0))
+    model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(DEV)
+
+    def make(ns=1.0, m=model):
+        sampler = te.LangevinDynamics(m, step_size=0.01, noise_scale=ns, device=DEV, rng="native")
+        return te.ContrastiveDivergence(m, sampler, k_steps=k, persistent=True, buffer_size=n, init_steps=0,
+                                        new_sample_ratio=0.0, device=DEV)
+
+    x = torch.randn(n, d, device=DEV)
+    a, b = make(), make()
+    ga, gb = torch.Generator(DEV).manual_seed(0), torch.Generator(DEV).manual_seed(0)
+    loss, neg = a(x, generator=ga)
+    start = b.get_start_points(x, generator=gb)
+    neg_b = b.sampler.sample(x=start, n_steps=k, generator=gb)
+    b.update_buffer(neg_b)
+    assert torch.equal(neg, neg_b) and torch.equal(a.replay_buffer, neg) and a._buffer_ptr_int == 0
     assert torch.isfinite(neg).all() and torch.isfinite(loss)
     loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+    flat = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(DEV)
+    with torch.no_grad():
+        for p in flat.parameters():
+            p.zero_()
+    s = te.LangevinDynamics(flat, step_size=0.01, noise_scale=0.7, device=DEV, rng="native")
+    x0 = torch.randn(n, d, device=DEV)
+    dx = s.sample(x=x0, n_steps=k, generator=torch.Generator(DEV).manual_seed(3)) - x0
+    var = 2 * 0.01 * k * 0.7 ** 2
+    assert abs(dx.mean().item()) < 5e-4 and abs(dx.var().item() / var - 1.0) < 5e-3
+    assert abs(dx.var(dim=0).mean().item() / var - 1.0) < 5e-3 and abs((dx[:, :392] * dx[:, 392:]).mean().item()) < 5e-4
+
+    quiet = te.LangevinDynamics(model, step_size=0.01, noise_scale=1e-4, device=DEV, rng="native")
+    with torch.no_grad():
+        e0 = model(x0)
+        e1 = model(quiet.sample(x=x0, n_steps=k, generator=torch.Generator(DEV).manual_seed(4)))
+    assert (e1 < e0).float().mean().item() > 0.999
 
 
 @pytest.mark.parametrize("d,buffer_size,batch", [(784, 300, 300), (784, 700, 300), (64, 33000, 33000), (64, 40000, 4096),
