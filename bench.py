@@ -58,18 +58,57 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed region runs."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region: NVML polled every 2 ms from a thread
+    (the timed region of a multi-GPU run lasts only tens of milliseconds, far less than an nvidia-smi start-up);
+    `nvidia-smi -lms` is the fallback when the NVML binding is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
         self.lines = []
+        self.samples = []   # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _nvml_loop(self, handle):
+        nv = self.nvml
+        while not self.stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:  # noqa: BLE001  (older bindings)
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(mhz), int(reasons)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(v) for v in vis.split(",")] if vis and all(v.strip().isdigit() for v in vis.split(",")) else None
+            phys = ids[self.index] if ids and self.index < len(ids) else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.nvml = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(handle,), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
@@ -85,6 +124,10 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *exc):
+        self.stop.set()
+        if self.nvml is not None:
+            self.thread.join(timeout=1)
+            return
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -94,6 +137,16 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        if self.nvml is not None:
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+            sm = sorted(s[0] for s in self.samples)
+            mask = 0
+            for _, r in self.samples:
+                mask |= r
+            reasons = sorted(name for name, bit in self.REASON_BITS.items() if mask & bit)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml, 2 ms polling inside the timed region"}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -109,9 +162,10 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi"}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 20"}
 
 
 def dist_setup(n_gpus: int):

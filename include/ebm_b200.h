@@ -125,6 +125,15 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
                            uint64_t seed, uint64_t offset, const float* noise, float* traj, int32_t thin,
                            void* stream);
 
+/* Noise-free descent burst; replaces the loops of GradientDescentSampler.sample (x <- x - eta * grad E(x),
+ * samplers/gradient_descent.py:123-138) and NesterovSampler.sample (lookahead gradient + momentum, :258-276) for the
+ * elementwise energies (others: EBM_ERR_UNSUPPORTED).  momentum < 0 selects plain gradient descent, 0 <= momentum < 1
+ * Nesterov (the velocity starts at 0).  velocity: NULL or [n, dim] scratch that receives the final velocity (required
+ * for per-step schedules longer than 64 steps).  traj / thin / schedule_len as in ebm_langevin_burst_f32. */
+int ebm_descent_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                          const double* step_size_host, int32_t schedule_len, double momentum, float* velocity, float* traj,
+                          int32_t thin, void* stream);
+
 /* Same burst on one rank of a box whose chains are sharded over `world` GPUs, with the burst-end all-gather (the one
  * collective of the sharded path) fused into the kernel's final store: besides x_out[n, dim] the final state is written
  * at rows [row_offset, row_offset + n) of EVERY rank's gathered buffer.  peer_out_host[w] (host array of `world` device

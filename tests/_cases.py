@@ -95,3 +95,27 @@ def langevin_schedule(name, g):
     if name == "langevin_scheduled":
         return [float(v) for v in g["h_values"]], [float(v) for v in g["ns_values"]]
     return float(g["h"]), float(g["ns"])
+
+# noise-free descent samplers: (golden, momentum or None)
+DESCENT_CASES = ["gd_doublewell", "gd_rastrigin_traj", "nesterov_doublewell_sched", "nesterov_harmonic_traj", "gd_mlp"]
+
+
+def descent_setup(name, g):
+    """(oracle energy, step sizes, momentum, kwargs) of a descent golden."""
+    if name == "gd_mlp":
+        en = mlp_from(load("langevin_mlp_d784"), "silu")
+    elif "doublewell" in name:
+        en = E.DoubleWell(2.0, 1.0)
+    elif "rastrigin" in name:
+        en = E.Rastrigin(g["a"])
+    else:
+        en = E.Harmonic(g["kspring"])
+    hs = [float(v) for v in g["h_values"]] if "h_values" in g else {"gd_doublewell": 0.01, "gd_rastrigin_traj": 0.001,
+                                                                     "nesterov_harmonic_traj": 0.05, "gd_mlp": 0.05}[name]
+    mu = float(g["momentum"]) if "momentum" in g else None
+    kw = {}
+    if name == "gd_rastrigin_traj":
+        kw = dict(thin=3, return_trajectory=True, return_diagnostics=True)
+    if name == "nesterov_harmonic_traj":
+        kw = dict(thin=2, return_trajectory=True, return_diagnostics=True)
+    return en, hs, mu, kw

@@ -265,6 +265,38 @@ def main():
         extra[f"b{i}"] = l.bias.detach()
     langevin_case("langevin_mlp_d784", m, 40, 784, 4, 0.01, 1.0, 21, extra=extra)
 
+    # noise-free descent samplers (samplers/gradient_descent.py); deterministic, so only x0 and the outputs are stored
+    from torchebm.samplers import GradientDescentSampler, NesterovSampler
+
+    def descent_case(name, sampler, n, d, k, seed, extra=None, **kw):
+        x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(seed))
+        res = sampler.sample(x=x0, n_steps=k, **kw)
+        arrs = dict(x0=x0, k=k)
+        if isinstance(res, tuple):
+            arrs["out"] = res[0]
+            arrs["diag_energy"] = res[1]["energy"]
+        else:
+            arrs["out"] = res
+        arrs.update(extra or {})
+        save(name, **arrs)
+
+    descent_case("gd_doublewell", GradientDescentSampler(DoubleWellModel(2.0, 1.0), step_size=0.01), 64, 16, 25, 31)
+    descent_case("gd_rastrigin_traj", GradientDescentSampler(RastriginModel(10.0), step_size=0.001), 33, 7, 12, 32,
+                 thin=3, return_trajectory=True, return_diagnostics=True, extra=dict(a=10.0))
+    k = 70
+    hs = ExponentialDecayScheduler(start_value=0.005, decay_rate=0.97, min_value=0.0005)
+    hv = []
+    hs.reset()
+    for _ in range(k):
+        hv.append(hs.get_value()); hs.step()
+    hs.reset()
+    descent_case("nesterov_doublewell_sched", NesterovSampler(DoubleWellModel(2.0, 1.0), step_size=hs, momentum=0.9), 40, 10, k, 33,
+                 extra=dict(h_values=np.array(hv), momentum=0.9))
+    descent_case("nesterov_harmonic_traj", NesterovSampler(HarmonicModel(1.5), step_size=0.05, momentum=0.5), 20, 6, 9, 34,
+                 thin=2, return_trajectory=True, return_diagnostics=True, extra=dict(kspring=1.5, momentum=0.5))
+    # same 784-64-64-1 energy as langevin_mlp_d784 (its weights are stored there)
+    descent_case("gd_mlp", GradientDescentSampler(m, step_size=0.05), 8, 784, 3, 35)
+
 
 if __name__ == "__main__":
     main()

@@ -449,3 +449,26 @@ def test_host_buffer_entry_point_equals_device_burst(n, d, rng_name):
         ops.langevin_burst_host(desc, xh, oh, scratch, 9, 0.01, 1.0, mode, 77, 16)
         assert torch.equal(oh, want.cpu())
     assert torch.equal(xh, x0)
+
+
+def test_annealed_noise_schedule_reaching_zero_matches_reference_stream():
+    """annealed Langevin as EnergyMatchingLoss drives it (losses/energy_matching.py:341-364) -- a
+    noise_scale scheduler that reaches 0.0.  The reference still draws randn_like at sigma = 0 (base_integrator.py:
+    721-729), so the burst must keep consuming the generator and stay bit-identical to the oracle on CUDA."""
+    import torchebm_b200 as te
+
+    k = 12
+    x0 = torch.randn(3000, 24, device=DEV, generator=torch.Generator(DEV).manual_seed(2))
+    for model, en in ((te.DoubleWellModel(2.0, 1.0), E.DoubleWell(2.0, 1.0)), (te.HarmonicModel(1.5), E.Harmonic(1.5))):
+        sched = te.LinearScheduler(start_value=1.0, end_value=0.0, n_steps=8)   # 0.0 from step 8 on
+        s = te.LangevinDynamics(model, step_size=0.01, noise_scale=sched, device=DEV)
+        g1, g2 = torch.Generator(DEV).manual_seed(5), torch.Generator(DEV).manual_seed(5)
+        got = s.sample(x=x0, n_steps=k, generator=g1)
+        ref = te.LinearScheduler(start_value=1.0, end_value=0.0, n_steps=8)
+        ns = []
+        for _ in range(k):
+            ns.append(ref.get_value())
+            ref.step()
+        assert ns[-1] == 0.0
+        want = olang.sample(en, x0, k, 0.01, ns, generator=g2)
+        assert torch.equal(got, want) and g1.get_offset() == g2.get_offset()

@@ -50,6 +50,29 @@ def _worker(rank, world, port, n_total, d, k, result_dir):
                 want = gather_chains(want_local)
                 results[f"{name}_{rng_mode}"] = bool(torch.equal(local, want_local) and torch.equal(buf.tensor, want))
                 buf.barrier()  # nobody may overwrite a peer's buffer before that peer has compared it
+        # copy-engine gather (MLP bursts): DMA pushes on a side stream while the next burst runs with one SM left free
+        mlp = te.MLPEnergy(dim=d, hidden=64, activation="silu").to(dev)
+        mlp.sm_margin = 1
+        desc = te.energy_descriptor(mlp, d, dev)
+        assert desc.c.sm_margin == 1
+        buf = PeerGatherBuffer(n_total, d, dev)
+        side = torch.cuda.Stream(device=dev)
+        ok = True
+        prev = None
+        for it in range(3):
+            local = ops.langevin_burst(desc, x_local, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=8 * it)
+            ready = torch.cuda.Event()
+            ready.record()
+            local.record_stream(side)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                buf.push(local)
+            prev = local
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        want = gather_chains(prev)
+        ok = bool(torch.equal(buf.tensor, want))
+        results["mlp_push"] = ok
         torch.save(results, os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()

@@ -146,3 +146,22 @@ def test_pcd_fifo_wraparound_matches_reference():
         assert torch.equal(buf.buffer, g["bufs"][it])
         assert buf.ptr == int(g["ptrs"][it])
     assert list(g["ptrs"].tolist()) == [16, 32, 48, 14, 30]
+
+
+@pytest.mark.parametrize("name", C.DESCENT_CASES)
+def test_descent_oracle_matches_reference_golden(name):
+    """GradientDescentSampler / NesterovSampler restatement vs the unmodified reference: bit-exact (autograd gradient;
+    closed forms bit-exact too for the elementwise energies)."""
+    from oracle import descent as odesc
+
+    g = C.load(name)
+    en, hs, mu, kw = C.descent_setup(name, g)
+    res = odesc.sample(en, g["x0"], int(g["k"]), hs, mu, **kw)
+    out = res[0] if isinstance(res, tuple) else res
+    assert torch.equal(out, g["out"])
+    if isinstance(res, tuple):
+        assert torch.equal(res[1]["energy"], g["diag_energy"])
+    if name != "gd_mlp":
+        res2 = odesc.sample(en, g["x0"], int(g["k"]), hs, mu, closed_form=True, **kw)
+        out2 = res2[0] if isinstance(res2, tuple) else res2
+        assert torch.equal(out2, g["out"])

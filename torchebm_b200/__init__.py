@@ -10,11 +10,12 @@ from .core import (BaseModel, BaseScheduler, ConstantScheduler, CosineScheduler,
                    MLPEnergy, RastriginModel, energy_descriptor, mark_mlp_energy)
 from .integrators import EulerMaruyamaIntegrator, LeapfrogIntegrator, energy_drift
 from .losses import BaseContrastiveDivergence, ContrastiveDivergence
-from .samplers import BaseSampler, HamiltonianMonteCarlo, LangevinDynamics
+from .samplers import BaseSampler, GradientDescentSampler, HamiltonianMonteCarlo, LangevinDynamics, NesterovSampler
 
 __all__ = [
     "BaseModel", "BaseScheduler", "ConstantScheduler", "CosineScheduler", "DoubleWellModel", "ExponentialDecayScheduler",
     "GaussianModel", "HarmonicModel", "LinearScheduler", "MixtureOfGaussiansModel", "MLPEnergy", "RastriginModel",
     "energy_descriptor", "mark_mlp_energy", "EulerMaruyamaIntegrator", "LeapfrogIntegrator", "energy_drift",
     "BaseContrastiveDivergence", "ContrastiveDivergence", "BaseSampler", "HamiltonianMonteCarlo", "LangevinDynamics",
+    "GradientDescentSampler", "NesterovSampler",
 ]

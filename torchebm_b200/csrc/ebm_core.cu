@@ -271,6 +271,54 @@ static int langevin_dispatch(const LangevinCall& c) {
   return EBM_ERR_INVALID;
 }
 
+template <class ElemE>
+static int launch_descent_elem(const ElemE& en, const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n,
+                               int32_t n_steps, const double* hs, int32_t schedule_len, double momentum, float* velocity,
+                               float* traj, int32_t thin, cudaStream_t st) {
+  DescentElemParams P;
+  memset(&P, 0, sizeof(P));
+  P.numel = (long long)n * e->dim;
+  P.d = e->dim;
+  P.thin = thin;
+  P.n_kept = n_steps / thin;
+  P.traj = traj;
+  P.nesterov = momentum >= 0.0 ? 1 : 0;
+  P.mu = (float)(momentum >= 0.0 ? momentum : 0.0);
+  const unsigned long long blocks = ((unsigned long long)(P.numel + 3) / 4 + 255) / 256;
+  if (blocks > 0x7fffffffull) { set_error("too many elements"); return EBM_ERR_UNSUPPORTED; }
+  const bool uniform = schedule_len == 1;
+  int done = 0;
+  const float* src = x_in;
+  while (done < n_steps) {
+    const int chunk = uniform ? n_steps : ((n_steps - done < kSchedChunk) ? (n_steps - done) : kSchedChunk);
+    StepTable tab;
+    memset(&tab, 0, sizeof(tab));
+    if (uniform) { tab.h[0] = (float)hs[0]; tab.mask = 0; }
+    else { for (int i = 0; i < chunk; ++i) tab.h[i] = (float)hs[done + i]; tab.mask = ~0; }
+    P.x_in = src;
+    P.x_out = x_out;
+    P.n_steps = chunk;
+    P.thin_start = thin - (done % thin);
+    P.kept_base = done / thin;
+    const bool more = done + chunk < n_steps;
+    P.v_in = done > 0 ? velocity : nullptr;            // the burst starts from v = 0 (gradient_descent.py:238)
+    P.v_out = (more || velocity) ? velocity : nullptr;
+    if (P.nesterov && more && !velocity) { set_error("a scheduled Nesterov burst longer than %d steps needs a velocity buffer", kSchedChunk); return EBM_ERR_INVALID; }
+    if (P.nesterov) {
+      if (traj) descent_elem_kernel<ElemE, true, true><<<(unsigned)blocks, 256, 0, st>>>(P, en, tab);
+      else      descent_elem_kernel<ElemE, true, false><<<(unsigned)blocks, 256, 0, st>>>(P, en, tab);
+    } else {
+      if (traj) descent_elem_kernel<ElemE, false, true><<<(unsigned)blocks, 256, 0, st>>>(P, en, tab);
+      else      descent_elem_kernel<ElemE, false, false><<<(unsigned)blocks, 256, 0, st>>>(P, en, tab);
+    }
+    int rc = launch_status("descent_elem_kernel");
+    if (rc) return rc;
+    done += chunk;
+    src = x_out;
+  }
+  return 0;
+}
+
 int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                              cudaStream_t st);  // ebm_mlp.cu
 
@@ -513,6 +561,28 @@ int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, 
   EBM_CUDA(cudaMemcpyAsync(x_out_host, scratch_dev, bytes, cudaMemcpyDeviceToHost, st));
   EBM_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+int ebm_descent_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                          const double* step_size_host, int32_t schedule_len, double momentum, float* velocity, float* traj,
+                          int32_t thin, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x_in && x_out && n > 0, "x_in/x_out must be non-null and n positive");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(step_size_host, "step sizes must be non-null");
+  EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
+  EBM_CHECK_ARG(thin >= 1, "thin must be >= 1");
+  EBM_CHECK_ARG(momentum < 1.0, "momentum must be in [0, 1) (negative = plain gradient descent)");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (e->kind) {
+    case EBM_ENERGY_DOUBLE_WELL: return launch_descent_elem(make_dw(e), e, x_in, x_out, n, n_steps, step_size_host, schedule_len, momentum, velocity, traj, thin, st);
+    case EBM_ENERGY_HARMONIC: return launch_descent_elem(make_harm(e), e, x_in, x_out, n, n_steps, step_size_host, schedule_len, momentum, velocity, traj, thin, st);
+    case EBM_ENERGY_RASTRIGIN: return launch_descent_elem(make_rast(e), e, x_in, x_out, n, n_steps, step_size_host, schedule_len, momentum, velocity, traj, thin, st);
+    default:
+      set_error("descent bursts are fused for the elementwise energies only (kind %d)", e->kind);
+      return EBM_ERR_UNSUPPORTED;
+  }
 }
 
 int ebm_pcd_gather_f32(const float* buffer, int64_t buffer_rows, int64_t row_elems, const int64_t* idx, int64_t batch,

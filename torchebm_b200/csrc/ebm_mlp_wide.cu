@@ -454,7 +454,6 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     // widest aligned access every pointer of this launch allows
     const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj | (uintptr_t)P.x_out2;
     const int vec = (P.d % 8 == 0 && (ptr_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (ptr_bits & 15) == 0) ? 1 : 0);
-    const long long numel = P.n * P.d;
     uint32_t acc_par = 0, g_par = 0;  // g_par: bit b = parity of g_full[b]
 
     for (int tile = units->t_last; tile >= units->t_first; --tile) {
@@ -465,8 +464,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       if (s0 > 0) mlp_unit_acquire(P.sched, kWdEpiWarps);
       const float* x0src = (s0 == 0) ? P.x_in : P.x_out;
       // row of the launch's input that holds this chain (replay-buffer gather fused into the first load)
-      const long long srow = (P.row_index && rv) ? P.row_index[grow] : grow;
-      const long long row0 = (s0 == 0) ? srow : grow;
+      const long long row0 = (s0 == 0 && P.row_index && rv) ? P.row_index[grow] : grow;
       // prologue: publish the unit's initial state chunk by chunk
       for (int c = 0; c < NC; ++c) {
         const int col0 = c * kWdChunk + 16 * cg;
@@ -480,15 +478,14 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         wd_publish(xa_full + 8 * xb);
       }
       int until_keep = P.thin - ((P.step_base + s0) % P.thin), kept = (P.step_base + s0) / P.thin;
-      RngStream rs;
-      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode;
-      rs.ctr_base = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
+      // only the stepping counter lives in registers; everything else of the stream is read from the parameters
+      unsigned long long ctr_base = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
 
       for (int k = s0; k < s1; ++k) {
         const int ti = k & tab.mask;
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
         const float* xsrc = (k == 0) ? P.x_in : P.x_out;
-        const long long xrow = (k == 0) ? srow : grow;
+        const long long xrow = (k == 0 && P.row_index && rv) ? P.row_index[grow] : grow;
         const bool final_step = P.x_out2 && (k == K - 1);
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM [256, 384)
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
@@ -546,12 +543,12 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           float eps[16];
           if (active) {
             const long long li0 = grow * P.d + col0;
-            if (rs.mode == 2 && P.d % 4 == 0 && col0 + 16 <= P.d) {
+            if (P.rng.mode == 2 && P.d % 4 == 0 && col0 + 16 <= P.d) {
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4) {
                 const uint64_t qi = (uint64_t)(li0 + 4 * q4) >> 2;
-                const uint4 w = philox4x32_10((uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)rs.ctr_base,
-                                              (uint32_t)(rs.ctr_base >> 32), rs.k0, rs.k1);
+                const uint4 w = philox4x32_10((uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)ctr_base,
+                                              (uint32_t)(ctr_base >> 32), P.rng.k0, P.rng.k1);
                 const float4 nn = normal4_fast(w);
                 eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
               }
@@ -560,7 +557,15 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
               for (int i = 0; i < 16; ++i) {
                 const bool in = rv && (col0 + i) < P.d;
                 float ev = 0.0f;
-                if (in) ev = (rs.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
+                if (in) {
+                  if (P.rng.mode == 0) {
+                    ev = P.noise[(long long)k * (P.n * P.d) + li0 + i];
+                  } else {
+                    RngStream rs;
+                    rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = ctr_base;
+                    ev = normal_for_element(rs, (uint64_t)(li0 + i));
+                  }
+                }
                 eps[i] = ev;
               }
             }
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
             if (keep_now) wd_store_x16(P.traj, (grow * P.n_kept + (kept - 1)) * P.d, col0, P.d, rv, vec, xc);
           }
         }
-        rs.ctr_base += P.rng.ctr_step;
+        ctr_base += P.rng.ctr_step;
       }
       if (s1 < K) mlp_unit_release(P.sched);  // the rest of this tile's burst runs on the next CTA
     }

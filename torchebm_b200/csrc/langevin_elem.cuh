@@ -163,4 +163,74 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
   }
 }
 
+// ---- noise-free descent bursts (GradientDescentSampler / NesterovSampler, samplers/gradient_descent.py:123-138,
+// 258-276) for the elementwise energies: one thread owns 4 consecutive elements for all K steps.  The reference's
+// `torch.sub(x, grad, alpha=eta)`, `torch.add(x, v, alpha=mu)` and `v.mul_(mu).sub_(grad, alpha=eta)` are single-rounding
+// fused multiply-adds in ATen (CPU and CUDA), so the updates here are explicit fmaf.
+struct DescentElemParams {
+  const float* x_in;
+  float* x_out;
+  float* traj;        // [n, n_kept, d] or null
+  long long numel;
+  int d, n_steps, thin, n_kept, thin_start, kept_base;
+  int nesterov;       // 0: gradient descent, 1: Nesterov momentum
+  float mu;
+  const float* v_in;  // Nesterov: velocity carried between launches of one burst (null = zeros)
+  float* v_out;       // Nesterov: velocity after this launch (null = not needed)
+};
+
+template <class EnergyT, bool NESTEROV, bool TRAJ>
+__global__ void __launch_bounds__(256) descent_elem_kernel(const __grid_constant__ DescentElemParams P, const EnergyT en,
+                                                           const __grid_constant__ StepTable tab) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = 4 * q;
+  if (i0 >= P.numel) return;
+  float x[4], v[4];
+  bool ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ok[i] = i0 + i < P.numel;
+    x[i] = ok[i] ? P.x_in[i0 + i] : 0.0f;
+    v[i] = (NESTEROV && ok[i] && P.v_in) ? P.v_in[i0 + i] : 0.0f;
+  }
+  long long tbase[4];
+  if (TRAJ) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = (i0 + i) / P.d;
+      tbase[i] = r * (long long)P.n_kept * P.d + ((i0 + i) - r * P.d);
+    }
+  }
+  int until_keep = P.thin_start, kept = P.kept_base;
+  for (int k = 0; k < P.n_steps; ++k) {
+    const float eta = tab.h[k & tab.mask];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (NESTEROV) {
+        const float look = __fmaf_rn(P.mu, v[i], x[i]);          // torch.add(x, v, alpha=mu)
+        const float g = en.grad(look);
+        v[i] = __fmaf_rn(-eta, g, __fmul_rn(v[i], P.mu));       // v.mul_(mu).sub_(grad, alpha=eta)
+        x[i] = __fadd_rn(x[i], v[i]);
+      } else {
+        x[i] = __fmaf_rn(-eta, en.grad(x[i]), x[i]);             // torch.sub(x, grad, alpha=eta)
+      }
+    }
+    if (TRAJ && --until_keep == 0) {
+      until_keep = P.thin;
+      if (kept < P.n_kept) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ok[i]) P.traj[tbase[i] + (long long)kept * P.d] = x[i];
+      }
+      ++kept;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!ok[i]) continue;
+    P.x_out[i0 + i] = x[i];
+    if (NESTEROV && P.v_out) P.v_out[i0 + i] = v[i];
+  }
+}
+
 }  // namespace ebm

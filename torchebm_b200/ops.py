@@ -132,6 +132,24 @@ def langevin_burst_gather(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int,
     return out
 
 
+def descent_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_sizes: Sequence[float], *,
+                  momentum: Optional[float] = None, traj: Optional[torch.Tensor] = None, thin: int = 1,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K noise-free descent steps (momentum None: gradient descent; else Nesterov starting from zero velocity)."""
+    x = _req(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    assert len(step_sizes) in (1, n_steps)
+    hs = _lib.doubles(list(step_sizes))
+    vel = torch.empty_like(x) if (momentum is not None and len(step_sizes) > 1 and n_steps > 64) else None
+    with torch.cuda.device(x.device):
+        rc = _lib.load().ebm_descent_burst_f32(C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs,
+                                               len(step_sizes), -1.0 if momentum is None else float(momentum), _ptr(vel),
+                                               _ptr(traj), int(thin), _stream(x.device))
+    _lib.check(rc, "ebm_descent_burst_f32")
+    return out
+
+
 def leapfrog(desc: EnergyDescriptor, x: torch.Tensor, p: torch.Tensor, step_size: float, n_steps: int,
              mass=None, safe: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     x, p = _req(x, "x"), _req(p, "p")

@@ -382,3 +382,76 @@ class HamiltonianMonteCarlo(BaseSampler):
             self.step_schedulers()
         out = traj if return_trajectory else x
         return (out, diag) if return_diagnostics else out
+
+
+class _DescentSampler(BaseSampler):
+    """Shared body of the noise-free samplers (samplers/gradient_descent.py:16-281): elementwise library energies run as
+    one fused burst (`ops.descent_burst`); every other energy steps through its own gradient (the library's kernels for
+    recognised energies, autograd otherwise) with the reference's ATen update ops."""
+
+    _momentum: Optional[float] = None
+
+    @torch.no_grad()
+    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[Union[int, Tuple[int, ...]]] = None,
+               n_steps: int = 100, n_samples: int = 1, thin: int = 1, return_trajectory: bool = False,
+               return_diagnostics: bool = False, reset_schedulers: bool = True, *,
+               model_kwargs: Optional[Dict[str, Any]] = None, generator: Optional[torch.Generator] = None):
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        self._require_cuda_fp32()
+        if reset_schedulers:
+            self.reset_schedulers()
+        x = self._init_state(x, dim, n_samples, generator)
+        model_kwargs = self._prepare_model_kwargs(model_kwargs)
+        n, data_shape = x.shape[0], x.shape[1:]
+        n_kept = n_steps // thin
+        traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
+        diag = {"energy": torch.empty(n_kept, dtype=self.dtype, device=self.device)} if return_diagnostics else None
+        desc = self._descriptor(x, model_kwargs)
+        mu = self._momentum
+        if desc is not None and desc.kind in ("double_well", "harmonic", "rastrigin") and n_steps > 0 and not return_diagnostics:
+            vals, _ = self._advance_schedules(("step_size",), n_steps)
+            out = ops.descent_burst(desc, x.contiguous(), n_steps, vals["step_size"], momentum=mu, traj=traj, thin=thin)
+            return traj if return_trajectory else out
+        # step by step (diagnostics need the energy of every kept state; other energies have no fused descent kernel)
+        v = torch.zeros_like(x) if mu is not None else None
+        keep = 0
+        for i in range(n_steps):
+            eta = self.get_scheduled_value("step_size")
+            if mu is None:
+                x = torch.sub(x, self._model_gradient(x, model_kwargs), alpha=eta)
+            else:
+                lookahead = torch.add(x, v, alpha=mu)
+                v.mul_(mu).sub_(self._model_gradient(lookahead, model_kwargs), alpha=eta)
+                x = x + v
+            if (i + 1) % thin == 0:
+                if traj is not None:
+                    traj[:, keep] = x
+                if diag is not None:
+                    diag["energy"][keep] = self._model_energy(x, model_kwargs).mean()
+                keep += 1
+            self.step_schedulers()
+        out = traj if return_trajectory else x
+        return (out, diag) if return_diagnostics else out
+
+
+class GradientDescentSampler(_DescentSampler):
+    """samplers/gradient_descent.py:16-140: x <- x - eta * grad E(x)."""
+
+    def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3, dtype: torch.dtype = torch.float32,
+                 device: Optional[Union[str, torch.device]] = None):
+        super().__init__(model=model, dtype=dtype, device=device)
+        self._register_param("step_size", step_size, positive=True)
+
+
+class NesterovSampler(_DescentSampler):
+    """samplers/gradient_descent.py:143-276: v <- mu v - eta grad E(x + mu v); x <- x + v."""
+
+    def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3, momentum: float = 0.9,
+                 dtype: torch.dtype = torch.float32, device: Optional[Union[str, torch.device]] = None):
+        super().__init__(model=model, dtype=dtype, device=device)
+        if not (0 <= momentum < 1):
+            raise ValueError("momentum must be in [0, 1)")
+        self.momentum = momentum
+        self._momentum = float(momentum)
+        self._register_param("step_size", step_size, positive=True)
