@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the fused MCMC negative-sampling hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5|mlp128]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5|mlp128]
 
 One bench "step" = one pass of the hot path over one batch: a K-step fused burst through the sampler-level
 API (`ops.langevin_burst` / `ops.hmc_burst`, i.e. one C-ABI call, one kernel launch).  Headline workload =
@@ -33,6 +33,8 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (description, n_chains, dim, k)
+    "c1": ("LangevinDynamics GaussianModel(mean=0, cov=[[1,.8],[.8,1]]) dim=2 n_chains=1024 k=100 step_size=0.01 "
+           "(examples/10-sampling/01-mcmc/01-langevin-101; the reference's own CPU-runnable case)", 1024, 2, 100),
     "c2": ("LangevinDynamics DoubleWell(2.0,1.0) dim=128 n_chains=65536 k=500 step_size=0.01 noise_scale=1.0", 65536, 128, 500),
     "mlp128": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01", 65536, 128, 100),
     "mlp128_fp32": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (fp32 FFMA kernel)", 65536, 128, 100),
@@ -193,6 +195,18 @@ def make_workload(name: str, n_local: int, dev):
     _, _, d, k = WORKLOADS[name]
     if name == "c2":
         model = te.DoubleWellModel(2.0, 1.0)
+        desc = te.energy_descriptor(model, d, dev)
+        inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
+
+        def step(x, out, it, kev=None):
+            if kev: kev[0].record()
+            ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            if kev: kev[1].record()
+            return 1, out
+
+        return step, desc, model, 8 * d, k
+    if name == "c1":
+        model = te.GaussianModel(torch.zeros(2), torch.tensor([[1.0, 0.8], [0.8, 1.0]])).to(dev)
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_TORCH)
 
@@ -450,8 +464,9 @@ def run_ours(args):
                      "note": "SURVEY 8(d) streaming model: 8*D bytes per chain-step (16*D per HMC leapfrog step); the burst "
                              "keeps the chain in registers, so real DRAM traffic is 8*D*N bytes per BURST and the kernel is "
                              "instruction-issue bound; see DESIGN.md and profiles/"})
-    if args.workload in ("c2", "mlp128", "c3") and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=args.cpu_k if args.workload == "c2" else 2)
+    if args.workload in ("c1", "c2", "mlp128", "c3") and world == 1 and not args.no_cpu_baseline:
+        k_cpu = {"c1": k, "c2": args.cpu_k}.get(args.workload, 2)   # C1 runs in full on the CPU (2 ms of GPU work)
+        line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=k_cpu, repeats=20 if args.workload == "c1" else 1)
         line["torch_cuda_baseline"] = torch_cuda_baseline(dev, args.workload)
     print(json.dumps(line))
 
@@ -479,6 +494,8 @@ def _oracle_energy(workload, device="cpu"):
         return E.make_mlp(128, (128, 128), "silu", seed=0).to(device)
     if workload in ("c3", "c5"):
         return E.make_mlp(784, (128, 128), "silu", seed=0).to(device)
+    if workload == "c1":
+        return E.Gaussian(torch.zeros(2), torch.tensor([[1.0, 0.8], [0.8, 1.0]])).to(device)
     return E.DoubleWell(2.0, 1.0)
 
 
@@ -526,14 +543,14 @@ def run_reference(args):
         return
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is one CPU job that may use the whole host
     torch.set_num_threads(os.cpu_count() or 1)
-    wl = args.workload if args.workload in ("c2", "c3", "c5", "mlp128") else "c2"
+    wl = args.workload if args.workload in ("c1", "c2", "c3", "c5", "mlp128") else "c2"
     desc_text, n, d, k = WORKLOADS[wl]
     from oracle import langevin as olang
 
     en = _oracle_energy(wl)
     x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).clamp_(-3.0, 3.0)
     gen = torch.Generator().manual_seed(1)
-    ks = args.cpu_k if wl == "c2" else 2
+    ks = {"c1": k, "c2": args.cpu_k}.get(wl, 2)
     for _ in range(args.warmup):
         olang.sample(en, x0, ks, 0.01, 1.0, generator=gen)
     t0 = time.perf_counter()
