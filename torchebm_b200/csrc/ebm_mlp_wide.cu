@@ -60,8 +60,7 @@ struct WdSmem {
   static constexpr int xa_full = ring_empty + kWdStages;     // [2], 16 epilogue warps
   static constexpr int xa_empty = xa_full + 2;        // [2], tcgen05.commit
   static constexpr int g_full = xa_empty + 2;         // [2], tcgen05.commit
-  static constexpr int g_empty = g_full + 2;          // [2], 16 epilogue warps: G buffer read into registers
-  static constexpr int a_chunk = g_empty + 2;         // [8], 4 warps each
+  static constexpr int a_chunk = g_full + 2;          // [8], 4 warps each
   static constexpr int acc_full = a_chunk + 8;        // tcgen05.commit
   static constexpr int n_bars = acc_full + 1;
   static constexpr int tmem_slot = bars + n_bars * 8;
@@ -293,8 +292,6 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     }
     mbar_init(wd_bar(smem, WdSmem::g_full + 0), 1);
     mbar_init(wd_bar(smem, WdSmem::g_full + 1), 1);
-    mbar_init(wd_bar(smem, WdSmem::g_empty + 0), kWdEpiWarps);
-    mbar_init(wd_bar(smem, WdSmem::g_empty + 1), kWdEpiWarps);
     for (int c = 0; c < 8; ++c) mbar_init(wd_bar(smem, WdSmem::a_chunk + c), 4);
     mbar_init(wd_bar(smem, WdSmem::acc_full), 1);
     fence_mbar_init();
@@ -349,7 +346,6 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       const uint32_t core_col = kWdM * 16;  // bytes between 8-column core blocks (R = 128 rows)
       uint32_t it = 0;                        // ring item counter (consumer side)
       uint32_t xcnt = 0, a_par = 0;         // xcnt: running count of published state chunks (buffer = xcnt & 1)
-      uint32_t ge_par = 0;                  // bit b = parity of g_empty[b]
       auto ring_wait = [&](uint32_t item) { mbar_wait(wd_bar(smem, WdSmem::ring_full + item % kWdStages), (item / kWdStages) & 1); };
       auto ring_release = [&](uint32_t item) { mma_commit(wd_bar(smem, WdSmem::ring_empty + item % kWdStages)); };
       auto stage_addr = [&](uint32_t item) { return ring + (item % kWdStages) * kWdStageBytes; };
@@ -422,16 +418,11 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           gemm4_chunk(it, 0);
           if (NC > 1) { ring_wait(it + 1); gemm4_chunk(it + 1, 1); }
           for (int c = 0; c < NC; ++c) {
-            // G[c & 1] is free as soon as every epilogue warp holds G_c in registers -- well before the updated chunk
-            // is published -- so the gradient chunk after next is issued first; the forward product can wait
-            mbar_wait(wd_bar(smem, WdSmem::g_empty + (c & 1)), (ge_par >> (c & 1)) & 1);
-            ge_par ^= 1u << (c & 1);
-            tcgen05_fence_after();
-            if (c + 2 < NC) { ring_wait(it + c + 2); gemm4_chunk(it + c + 2, c + 2); }
-            xa_wait();                                                       // x'_c published
+            xa_wait();                                                       // x'_c published, G[c & 1] drained
             if (!last) gemm1_chunk(it + c, c);
             xa_release();
             ring_release(it + c);
+            if (c + 2 < NC) { ring_wait(it + c + 2); gemm4_chunk(it + c + 2, c + 2); }
           }
           it += NC;
           if (!last) mma_commit(wd_bar(smem, WdSmem::acc_full));
@@ -582,18 +573,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           mbar_wait(wd_bar(smem, WdSmem::g_full + (c & 1)), (g_par >> (c & 1)) & 1);
           g_par ^= 1u << (c & 1);
           tcgen05_fence_after();
-          float g[16];
-          if (active) tmem_ld16(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
-          {  // G_c is in registers (tmem_ld16 waits for the load): hand the TMEM buffer back to the MMA thread
-            tcgen05_fence_before();
-            __syncwarp();
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t.reg .b64 st;\n\t"
-                "elect.sync _|p, 0xffffffff;\n\t"
-                "@p mbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(wd_bar(smem, WdSmem::g_empty + (c & 1)))
-                : "memory");
-          }
           if (active) {
+            float g[16];
+            tmem_ld16(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
             if (P.has_clamp) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
