@@ -51,9 +51,10 @@ struct HmcCall {
   cudaStream_t st;
 };
 
-template <class RowE>
-static int launch_hmc(const RowE& en, const HmcCall& c, HmcParams& P) {
-  const DeviceInfo& di = device_info(current_device());
+// the proposal loop is launched in chunks of at most kSchedChunk proposals (per-proposal step-size table); `launch`
+// runs one chunk
+template <class Launch>
+static int hmc_chunks(const HmcCall& c, HmcParams& P, Launch launch) {
   const bool uniform = c.schedule_len == 1;
   const long long numel = P.n * P.d;
   const float* noise_p = P.noise_p;
@@ -82,25 +83,35 @@ static int launch_hmc(const RowE& en, const HmcCall& c, HmcParams& P) {
       P.rng_p.ctr_base = c.offset / 4 + 2ull * done;
       P.rng_u.ctr_base = c.offset / 4 + 2ull * done + 1;
     }
-#define CALL(G, E)                                                                                  \
-  {                                                                                                 \
-    int ss;                                                                                         \
-    const size_t smem = row_smem_bytes(c.e, G, ss);                                                 \
-    if (smem > (size_t)di.max_smem_optin) { set_error("energy parameters need %zu B of shared memory", smem); return EBM_ERR_UNSUPPORTED; } \
-    P.scratch_stride = ss;                                                                          \
-    auto kern = hmc_kernel<RowE, G, E>;                                                             \
-    if (smem > 48 * 1024) EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<row_grid(di, P.n, G, 4), kRowThreads, smem, c.st>>>(en, P, tab);                         \
-  }
-    EBM_ROW_DISPATCH(c.e->dim, CALL);
-#undef CALL
-    int rc = launch_status("hmc_kernel");
+    int rc = launch(P, tab);
     if (rc) return rc;
     done += chunk;
     x_src = P.x_out;
   }
   return 0;
 }
+
+template <class RowE>
+static int launch_hmc(const RowE& en, const HmcCall& c, HmcParams& P) {
+  const DeviceInfo& di = device_info(current_device());
+  return hmc_chunks(c, P, [&](HmcParams& Pc, const HStepTable& tab) -> int {
+#define CALL(G, E)                                                                                  \
+  {                                                                                                 \
+    int ss;                                                                                         \
+    const size_t smem = row_smem_bytes(c.e, G, ss);                                                 \
+    if (smem > (size_t)di.max_smem_optin) { set_error("energy parameters need %zu B of shared memory", smem); return EBM_ERR_UNSUPPORTED; } \
+    Pc.scratch_stride = ss;                                                                         \
+    auto kern = hmc_kernel<RowE, G, E>;                                                             \
+    if (smem > 48 * 1024) EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<row_grid(di, Pc.n, G, 4), kRowThreads, smem, c.st>>>(en, Pc, tab);                       \
+  }
+    EBM_ROW_DISPATCH(c.e->dim, CALL);
+#undef CALL
+    return launch_status("hmc_kernel");
+  });
+}
+
+int hmc_mlp_launch(const EbmEnergyDesc* e, const HmcParams& P, const HStepTable& tab, cudaStream_t st);  // ebm_mlp.cu
 
 }  // namespace ebm
 
@@ -179,6 +190,13 @@ int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, i
     case EBM_ENERGY_RASTRIGIN: return launch_hmc(ElemRow<RastriginE>{make_rast(e)}, c, P);
     case EBM_ENERGY_GAUSSIAN: return launch_hmc(make_gauss(e), c, P);
     case EBM_ENERGY_MOG: return launch_hmc(make_mog(e), c, P);
+    case EBM_ENERGY_MLP:
+      if (e->dim > 128 || e->hidden1 > 128 || e->hidden2 > 128) {
+        set_error("hmc: MLP energies wider than 128 have no fused HMC kernel");
+        return EBM_ERR_UNSUPPORTED;
+      }
+      // fp32 FFMA kernel whatever e->precision says: accept decisions compare energies, which want full precision
+      return hmc_chunks(c, P, [&](HmcParams& Pc, const HStepTable& tab) -> int { return hmc_mlp_launch(e, Pc, tab, c.st); });
     default: set_error("hmc: energy kind %d has no fused kernel", e->kind); return EBM_ERR_UNSUPPORTED;
   }
 }

@@ -323,6 +323,208 @@ __global__ void __launch_bounds__(kMlpWarps * 32, 1) langevin_mlp_kernel(const _
   }
 }
 
+
+// ---- HMC on MLP energies (hmc.py:244-312 + leapfrog.py:160-185) -----------------------------------------------------
+// Same warp-owns-8-chains layout as the Langevin kernel above: per proposal the momentum draw, H0, L leapfrog steps
+// (one fused forward + input-backward per step: the force at the bottom of step l is the force at the top of step
+// l+1, and the forward pass of the last one is E(x')), H1, the Metropolis test and the select all happen in the warp;
+// x, p and the carried force live in registers.  The pre-proposal state is parked in x_out (rows are warp-private), and
+// the force at a restored state is recomputed at the top of the next proposal when any of the warp's rows rejected.
+__device__ __forceinline__ void mlp_force(float (&g)[kMlpRows][4]) {
+#pragma unroll
+  for (int r = 0; r < kMlpRows; ++r)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) g[r][v] = clamp_torch(-g[r][v], -kSafeClamp, kSafeClamp);   // safe=True, hmc.py:258-265
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kMlpWarps * 32, 1) hmc_mlp_kernel(const __grid_constant__ MlpParams M,
+                                                                    const __grid_constant__ HmcParams P,
+                                                                    const __grid_constant__ HStepTable tab) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const MlpSmem s = carve(smem, warp);
+  {
+    MlpSmem s0 = carve(smem, 0);
+    stage_all(s0, M);
+  }
+  const long long n_tiles = (P.n + kMlpTile - 1) / kMlpTile;
+  const long long numel = P.n * P.d;
+  const bool quad_rng = (P.d % 4 == 0);
+  float minv[4], msqrt[4], mraw[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int col = 4 * lane + v;
+    float mv = 1.0f;
+    if (P.mass.kind == 2 && col < P.d) mv = P.mass.vec[col];
+    mraw[v] = mv;
+    minv[v] = fmaxf(mv, 1e-10f);   // torch.clamp(mass, min=1e-10), leapfrog.py:174
+    msqrt[v] = sqrtf(mv);          // torch.sqrt(mass), hmc.py:129
+  }
+  auto kinetic = [&](const float (&p)[kMlpRows][4], float (&k_out)[kMlpRows]) {   // hmc.py:148-159
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float sq = __fmul_rn(p[r][v], p[r][v]);
+        acc += (P.mass.kind == 2) ? __fdiv_rn(sq, mraw[v]) : sq;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      acc = __fmul_rn(0.5f, acc);
+      if (P.mass.kind == 1) acc = __fdiv_rn(acc, P.mass.scalar);
+      k_out[r] = clamp_torch(acc, 0.0f, 1e10f);
+    }
+  };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * kMlpTile + warp * kMlpRows;
+    float x[kMlpRows][4], f[kMlpRows][4], p[kMlpRows][4], e_cur[kMlpRows], e_new[kMlpRows];
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) {
+      const long long row = row0 + r;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) x[r][v] = (row < P.n && 4 * lane + v < P.d) ? P.x_in[row * P.d + 4 * lane + v] : 0.0f;
+    }
+    RngStream rp, ru;
+    rp.k0 = P.rng_p.k0; rp.k1 = P.rng_p.k1; rp.T = P.rng_p.T; rp.mode = P.rng_p.mode; rp.ctr_base = P.rng_p.ctr_base;
+    ru.k0 = P.rng_u.k0; ru.k1 = P.rng_u.k1; ru.T = P.rng_u.T; ru.mode = P.rng_u.mode; ru.ctr_base = P.rng_u.ctr_base;
+    int until_keep = P.thin_start, kept = P.kept_base;
+    bool need_force = true;
+
+    for (int i = 0; i < P.n_prop; ++i) {
+      const float h = tab.h[i & tab.mask];
+      const float half_h = __fmul_rn(0.5f, h);
+      if (need_force) {   // E(x) and the force at the chain state (first proposal, or a row of this warp was restored)
+        mlp_grad_rows<ACT>(s, M, lane, x, f, true, e_cur);
+        mlp_force(f);
+        need_force = false;
+      }
+      // park the pre-proposal state and draw the momentum (hmc.py:245 / :92-134)
+#pragma unroll
+      for (int r = 0; r < kMlpRows; ++r) {
+        const long long row = row0 + r;
+        const bool rv = row < P.n;
+        const long long li0 = row * P.d + 4 * lane;
+        float eps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (rv && 4 * lane < P.d) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (4 * lane + v < P.d) P.x_out[li0 + v] = x[r][v];
+          if (P.rng_p.mode == 0) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (4 * lane + v < P.d) eps[v] = P.noise_p[(long long)i * numel + li0 + v];
+          } else if (P.rng_p.mode == 2 && quad_rng) {
+            const uint64_t q = (uint64_t)li0 >> 2;
+            const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rp.ctr_base,
+                                          (uint32_t)(rp.ctr_base >> 32), rp.k0, rp.k1);
+            const float4 nn = normal4(w);
+            eps[0] = nn.x; eps[1] = nn.y; eps[2] = nn.z; eps[3] = nn.w;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (4 * lane + v < P.d) eps[v] = normal_for_element(rp, (uint64_t)(li0 + v));
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (P.mass.kind == 1) eps[v] = __fmul_rn(eps[v], P.mass.sqrt_scalar);   // hmc.py:124
+          else if (P.mass.kind == 2) eps[v] = __fmul_rn(eps[v], msqrt[v]);         // hmc.py:133
+          p[r][v] = eps[v];
+        }
+      }
+      float k0[kMlpRows], h0[kMlpRows];
+      kinetic(p, k0);
+#pragma unroll
+      for (int r = 0; r < kMlpRows; ++r) h0[r] = __fadd_rn(clamp_torch(e_cur[r], -1e10f, 1e10f), k0[r]);   // hmc.py:247-256
+      // leapfrog (leapfrog.py:160-185), safe mode
+      for (int l = 0; l < P.n_leapfrog; ++l) {
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            p[r][v] = __fadd_rn(p[r][v], __fmul_rn(half_h, f[r][v]));   // p_half
+            float dx = __fmul_rn(h, p[r][v]);
+            if (P.mass.kind == 1) dx = __fdiv_rn(dx, P.mass.safe_scalar);
+            else if (P.mass.kind == 2) dx = __fdiv_rn(dx, minv[v]);
+            x[r][v] = (4 * lane + v < P.d) ? __fadd_rn(x[r][v], dx) : 0.0f;
+          }
+        mlp_grad_rows<ACT>(s, M, lane, x, f, true, e_new);
+        mlp_force(f);
+        bool dirty = false;
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            p[r][v] = __fadd_rn(p[r][v], __fmul_rn(half_h, f[r][v]));
+            const float xs = nan_to_num0(x[r][v]), ps = nan_to_num0(p[r][v]);
+            dirty |= (__float_as_uint(xs) != __float_as_uint(x[r][v]));
+            x[r][v] = xs;
+            p[r][v] = ps;
+          }
+        if (__any_sync(0xffffffffu, dirty)) {   // the reference recomputes the force at the sanitised state
+          mlp_grad_rows<ACT>(s, M, lane, x, f, true, e_new);
+          mlp_force(f);
+        }
+      }
+      // H1, Metropolis test (hmc.py:268-292)
+      float k1[kMlpRows];
+      kinetic(p, k1);
+      int n_acc = 0;
+      bool any_reject = false;
+#pragma unroll
+      for (int r = 0; r < kMlpRows; ++r) {
+        const long long row = row0 + r;
+        const bool rv = row < P.n;
+        const float h1 = __fadd_rn(clamp_torch(e_new[r], -1e10f, 1e10f), k1[r]);
+        const float dh = clamp_torch(__fsub_rn(h0[r], h1), -50.0f, 50.0f);
+        float a = expf(dh);
+        a = (a != a) ? a : fminf(a, 1.0f);   // clamp_(max=1.0) keeps NaN
+        float u = 0.0f;
+        if (rv) u = (P.rng_u.mode == 0) ? P.noise_u[(long long)i * P.n + row] : uniform_for_element(ru, (uint64_t)row);
+        const bool accepted = u < a;
+        if (accepted) {
+          e_cur[r] = e_new[r];
+          n_acc += rv ? 1 : 0;
+        } else {
+          any_reject = true;
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            x[r][v] = (rv && 4 * lane + v < P.d) ? P.x_out[row * P.d + 4 * lane + v] : 0.0f;
+        }
+      }
+      need_force = any_reject;   // warp-uniform: every lane saw the same per-row decisions
+      if (P.accept_count && lane == 0 && n_acc > 0) atomicAdd(P.accept_count + P.prop_base + i, n_acc);
+      rp.ctr_base += P.rng_p.ctr_step;
+      ru.ctr_base += P.rng_u.ctr_step;
+      if (P.traj && --until_keep == 0) {
+        until_keep = P.thin;
+        if (kept < P.n_kept) {
+#pragma unroll
+          for (int r = 0; r < kMlpRows; ++r) {
+            const long long row = row0 + r;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (row < P.n && 4 * lane + v < P.d) P.traj[(row * P.n_kept + kept) * P.d + 4 * lane + v] = x[r][v];
+          }
+        }
+        ++kept;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) {
+      const long long row = row0 + r;
+      if (row >= P.n) continue;
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (4 * lane + v < P.d) P.x_out[row * P.d + 4 * lane + v] = x[r][v];
+      if (P.energy_out && lane == 0) P.energy_out[row] = clamp_torch(e_cur[r], -1e10f, 1e10f);
+    }
+  }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(kMlpWarps * 32, 1) mlp_energy_grad_kernel(const __grid_constant__ MlpParams P) {
   extern __shared__ __align__(16) float smem[];
@@ -383,6 +585,24 @@ static int mlp_grid(const DeviceInfo& di, long long n) {
     case EBM_ACT_RELU: CALL(EBM_ACT_RELU); break;          \
     default: CALL(EBM_ACT_SOFTPLUS); break;                \
   }
+
+
+// one chunk of proposals of ebm_hmc_burst_f32 for an MLP energy (called from the chunk loop in ebm_hmc.cu)
+int hmc_mlp_launch(const EbmEnergyDesc* e, const HmcParams& P, const HStepTable& tab, cudaStream_t st) {
+  MlpParams M;
+  int rc = fill_mlp(e, M);
+  if (rc) return rc;
+  const DeviceInfo& di = device_info(current_device());
+#define CALL(A)                                                                                              \
+  {                                                                                                          \
+    auto kern = hmc_mlp_kernel<A>;                                                                           \
+    EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemBytes));   \
+    kern<<<mlp_grid(di, P.n), kMlpWarps * 32, kMlpSmemBytes, st>>>(M, P, tab);                               \
+  }
+  EBM_ACT_DISPATCH(e->activation, CALL);
+#undef CALL
+  return launch_status("hmc_mlp_kernel");
+}
 
 int mlp_wide_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                                   cudaStream_t st);  // ebm_mlp_wide.cu

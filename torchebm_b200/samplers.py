@@ -283,9 +283,9 @@ class HamiltonianMonteCarlo(BaseSampler):
         n, d = x.shape
         n_kept = n_steps // thin
         desc = self._descriptor(x, model_kwargs) if type(self.integrator) is LeapfrogIntegrator else None
-        if desc is None or desc.kind == "mlp":
-            # no fused HMC kernel for this energy (custom models, MLP energies, conditioning, custom symplectic
-            # integrators): the integrator-level path, hmc.py:244-312 step for step
+        if desc is None or (desc.kind == "mlp" and max(desc.c.dim, desc.c.hidden1, desc.c.hidden2) > 128):
+            # no fused HMC kernel for this energy (custom models, MLP energies wider than 128, conditioning, custom
+            # symplectic integrators): the integrator-level path, hmc.py:244-312 step for step
             return self._sample_opaque(x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator)
         x = x.contiguous()
         rng_mode = _lib.RNG_MODES[self.rng]
