@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the fused MCMC negative-sampling hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5|mlp128]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5|mlp128|hmc_mlp128]
 
 One bench "step" = one pass of the hot path over one batch: a K-step fused burst through the sampler-level
 API (`ops.langevin_burst` / `ops.hmc_burst`, i.e. one C-ABI call, one kernel launch).  Headline workload =
@@ -40,6 +40,8 @@ WORKLOADS = {
     "mlp128_fp32": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (fp32 FFMA kernel)", 65536, 128, 100),
     "mlp128_bf16": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (single-pass bf16)", 65536, 128, 100),
     "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
+    "hmc_mlp128": ("HamiltonianMonteCarlo MLP 128-128-128-1 SiLU dim=128 n_chains=65536 L=10, 1 proposal per step, "
+                   "step_size=0.05 (fused fp32 HMC kernel)", 65536, 128, 10),
     "c3": ("ContrastiveDivergence persistent=True negatives: replay-buffer gather -> LangevinDynamics MLP 784-128-128-1 SiLU "
            "k=20 step_size=0.01 -> FIFO write-back; n_chains=65536=buffer_size", 65536, 784, 20),
     # C5 = C3 sharded over the GPUs of one box: 65 536 chains PER GPU (524 288 at 8 GPUs), weak scaling
@@ -231,14 +233,18 @@ def make_workload(name: str, n_local: int, dev):
             return 1, out
 
         return step, desc, model, 8 * d, k
-    if name == "c4":
-        model = te.RastriginModel(10.0)
+    if name in ("c4", "hmc_mlp128"):
+        if name == "c4":
+            model, eps_h = te.RastriginModel(10.0), 0.01
+        else:
+            torch.manual_seed(0)
+            model, eps_h = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev), 0.05
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_hmc(dev, n_local, d, 1, _lib.RNG_TORCH)
 
         def step(x, out, it, kev=None):
             if kev: kev[0].record()
-            ops.hmc_burst(desc, x, 1, k, [0.01], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            ops.hmc_burst(desc, x, 1, k, [eps_h], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
             if kev: kev[1].record()
             return 1, out
 
@@ -437,7 +443,7 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload)
     line = {
-        "metric": METRIC if args.workload != "c4" else "hmc_leapfrog_chain_steps_per_sec",
+        "metric": METRIC if args.workload not in ("c4", "hmc_mlp128") else "hmc_leapfrog_chain_steps_per_sec",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong",
         "vs_baseline": None,
@@ -464,6 +470,8 @@ def run_ours(args):
                      "note": "SURVEY 8(d) streaming model: 8*D bytes per chain-step (16*D per HMC leapfrog step); the burst "
                              "keeps the chain in registers, so real DRAM traffic is 8*D*N bytes per BURST and the kernel is "
                              "instruction-issue bound; see DESIGN.md and profiles/"})
+    if args.workload in ("c4", "hmc_mlp128") and world == 1 and not args.no_cpu_baseline:
+        line["torch_cuda_baseline"] = torch_cuda_hmc_baseline(dev, args.workload)
     if args.workload in ("c1", "c2", "mlp128", "c3") and world == 1 and not args.no_cpu_baseline:
         k_cpu = {"c1": k, "c2": args.cpu_k}.get(args.workload, 2)   # C1 runs in full on the CPU (2 ms of GPU work)
         line["cpu_baseline"] = cpu_baseline(args.workload, k_sample=k_cpu, repeats=20 if args.workload == "c1" else 1)
@@ -474,6 +482,14 @@ def run_ours(args):
 def roofline(workload, peaks, peak_kind, achieved_gbs, traffic, algo_bytes, kernel_ms, units_per_launch):
     """HBM streaming model for the analytic paths; tensor-pipe model (4*(D*H + H*H + H) FLOP per chain-step,
     against the measured bf16 burst peak) for the MLP path."""
+    if workload == "hmc_mlp128":   # (L + 1) forward + input-backward evaluations per proposal of L leapfrog steps, fp32 FMA pipe
+        flops = 4 * (128 * 128 + 128 * 128 + 128) * units_per_launch * 11 / 10
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
+                "algorithmic_flops_per_launch": flops, "kernel_ms": kernel_ms,
+                "pipe_note": "this kernel runs on the fp32 FMA pipe (accept decisions want fp32 energies); the bf16 tensor peak "
+                             "is quoted only because it is the measured denominator available"}
     if workload.startswith("mlp128") or workload in ("c3", "c5"):
         d_in = 784 if workload in ("c3", "c5") else 128
         flops = 4 * (d_in * 128 + 128 * 128 + 128) * units_per_launch
@@ -535,6 +551,32 @@ def torch_cuda_baseline(dev, workload: str = "c2", k_sample: int = 20):
     return {"value": n * k_sample / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
             "what": "oracle (op-for-op restatement of the reference sampler, autograd gradient) on the same GPU",
             "sample": f"{n}x{d} chains, {k_sample} steps"}
+
+
+def torch_cuda_hmc_baseline(dev, workload: str):
+    """Reference HMC (oracle restatement: same torch ops, autograd gradients, 2 L gradient evaluations per proposal)
+    on the same GPU, on a bounded sample of the chains."""
+    from oracle import energies as E
+    from oracle import hmc as ohmc
+
+    _, n, d, L = WORKLOADS[workload]
+    n_s = min(n, 65536)
+    if workload == "c4":
+        en, h = E.Rastrigin(10.0), 0.01
+    else:
+        en, h = E.make_mlp(128, (128, 128), "silu", seed=0).to(dev), 0.05
+    x0 = torch.randn(n_s, d, device=dev)
+    gen = torch.Generator(dev).manual_seed(1)
+    ohmc.sample(en, x0, 1, h, L, generator=gen)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ohmc.sample(en, x0, 2, h, L, generator=gen)
+    b.record()
+    torch.cuda.synchronize()
+    return {"value": n_s * 2 * L / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
+            "what": "oracle (op-for-op restatement of the reference HMC sampler) on the same GPU",
+            "sample": f"{n_s}x{d} chains, 2 proposals of {L} leapfrog steps"}
 
 
 def run_reference(args):
