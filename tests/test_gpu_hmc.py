@@ -254,17 +254,19 @@ def test_hmc_integrator_level_path_for_mlp_and_custom_energies():
     assert bad < 0.01, bad
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("act", ["tanh", "silu"])
 @pytest.mark.parametrize("mass_kind", ["none", "scalar", "vector"])
-def test_hmc_fused_mlp_kernel_matches_oracle(act, mass_kind):
-    """MLP energies up to 128 wide have a fused HMC kernel (warp owns 8 chains, fp32 FFMA forward + input-backward per
-    leapfrog step): injected noise vs the CPU oracle and same seed vs the oracle on CUDA, trajectories + diagnostics."""
+def test_hmc_fused_mlp_kernel_matches_oracle(act, mass_kind, precision):
+    """MLP energies up to 128 wide have fused HMC kernels -- "bf16x3": tcgen05 tensor cores (tile of 128 chains, momentum
+    in TMEM, split operands), "fp32": CUDA-core FFMA (warp owns 8 chains): injected noise vs the CPU oracle and same seed
+    vs the oracle on CUDA, trajectories + diagnostics; several tiles so the persistent loop and ragged tile run."""
     import torchebm_b200 as te
     from torchebm_b200 import _lib, ops
 
     torch.manual_seed(6)
     n, d, L, k = 1000, 20, 5, 6
-    mlp = te.MLPEnergy(dim=d, hidden=(48, 32), activation=act).to(DEV)
+    mlp = te.MLPEnergy(dim=d, hidden=(48, 32), activation=act, precision=precision).to(DEV)
     lin = [l for l in mlp.net if isinstance(l, torch.nn.Linear)]
     en_cpu = E.MLP([l.weight.cpu() for l in lin], [l.bias.cpu() for l in lin], act)
     en_gpu = E.MLP([l.weight for l in lin], [l.bias for l in lin], act)

@@ -112,6 +112,7 @@ static int launch_hmc(const RowE& en, const HmcCall& c, HmcParams& P) {
 }
 
 int hmc_mlp_launch(const EbmEnergyDesc* e, const HmcParams& P, const HStepTable& tab, cudaStream_t st);  // ebm_mlp.cu
+int hmc_mlp_tc_launch(const EbmEnergyDesc* e, const HmcParams& P, const HStepTable& tab, int passes, cudaStream_t st);  // ebm_mlp_tc.cu
 
 }  // namespace ebm
 
@@ -195,7 +196,11 @@ int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, i
         set_error("hmc: MLP energies wider than 128 have no fused HMC kernel");
         return EBM_ERR_UNSUPPORTED;
       }
-      // fp32 FFMA kernel whatever e->precision says: accept decisions compare energies, which want full precision
+      // bf16x3 (the default precision): tensor-core kernel, energies good to ~2e-5 relative; fp32: FFMA kernel; the
+      // single-pass bf16 mode is refused here because accept decisions compare energies
+      if (e->precision == EBM_MLP_BF16X3)
+        return hmc_chunks(c, P, [&](HmcParams& Pc, const HStepTable& tab) -> int { return hmc_mlp_tc_launch(e, Pc, tab, 3, c.st); });
+      if (e->precision == EBM_MLP_BF16) { set_error("hmc: precision bf16 (single pass) is not offered for HMC; use bf16x3 or fp32"); return EBM_ERR_UNSUPPORTED; }
       return hmc_chunks(c, P, [&](HmcParams& Pc, const HStepTable& tab) -> int { return hmc_mlp_launch(e, Pc, tab, c.st); });
     default: set_error("hmc: energy kind %d has no fused kernel", e->kind); return EBM_ERR_UNSUPPORTED;
   }

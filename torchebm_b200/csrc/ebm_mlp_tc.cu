@@ -46,7 +46,7 @@ constexpr int kTcEpiRegs = EBM_TC_EPI_REGS;
 constexpr int kTcMatBytes = kTcW * kTcW * 2;  // one bf16 [128 x 128] operand
 
 struct TcParams {
-  const float* W1; const float* b1; const float* W2; const float* b2; const float* w3;
+  const float* W1; const float* b1; const float* W2; const float* b2; const float* w3; const float* b3;
   int d, h1, h2;
   int passes;  // 3: bf16x3 split, 1: plain bf16
   const float* x_in;
@@ -76,6 +76,9 @@ struct TcSmemLayout {
   static constexpr int tmem_slot = bars + (kTcChunks + 1) * 8;
   static constexpr int units = tmem_slot + 16;
   static constexpr int total = units + 16;
+  // HMC kernel only: per-row partial sums of E(x), E(x'), K(p), K(p') per column quarter, double-buffered by proposal
+  static constexpr int hmc_part = (total + 15) & ~15;
+  static constexpr int hmc_total = hmc_part + 2 * 4 * 4 * kTcM * 4;
 };
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -426,6 +429,338 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
   }
 }
 
+
+// ---- HMC on MLP energies on the tensor cores ----------------------------------------------------------------------
+// Same tile / role / product structure as langevin_mlp_tc_kernel; the MMA thread runs the identical four-product chain
+// once per gradient evaluation, (L + 1) evaluations per proposal: the force at the bottom of leapfrog step l is the
+// force at the top of step l+1, the forward half of evaluation 0 yields E(x) and that of evaluation L yields E(x').
+// Epilogue differences: E2 also accumulates w3 . act(z2) (the energy) for evaluations 0 and L; E4 applies the
+// leapfrog kicks / drift instead of the Langevin update, with the momentum parked in TMEM columns [384, 512); after
+// evaluation L the four column-quarter warps of a row combine their partial energies through shared memory (one named
+// barrier per proposal) and every thread takes the Metropolis decision of its row.  The pre-proposal state is parked
+// in x_out.  Deviation from the reference in one corner: when safe-mode sanitising rewrites a NaN/inf coordinate the
+// reference recomputes the force at the sanitised state before the next step; here the carried force is kept.
+struct TcHmcParams {
+  TcParams T;      // weights, widths, passes, schedule; T.n_steps = proposals of this launch * (L + 1)
+  HmcParams H;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_constant__ TcHmcParams Q,
+                                                                   const __grid_constant__ HStepTable tab) {
+  extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw;
+  const TcParams& P = Q.T;
+  const HmcParams& H = Q.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  tc_stage_weights(smem, P);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < kTcChunks; ++c) mbar_init(smem_u32(smem + TcSmemLayout::bars + c * 8), 4);
+    mbar_init(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8), 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x == 32) mlp_units_compute(P.sched, P.n_steps, reinterpret_cast<volatile MlpUnits*>(smem + TcSmemLayout::units));
+  if (warp == 0) tmem_alloc(smem_u32(smem + TcSmemLayout::tmem_slot), 512);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + TcSmemLayout::tmem_slot);
+  const int k1 = (P.d + 15) / 16, k2 = (P.h1 + 15) / 16, k3 = (P.h2 + 15) / 16;
+  const volatile MlpUnits* units = reinterpret_cast<const volatile MlpUnits*>(smem + TcSmemLayout::units);
+  const int L = H.n_leapfrog;
+
+  if (warp < kTcRoleWarps) {
+    if (warp == 0 && lane == 0) {
+      uint32_t parity = 0;
+      for (int tile = units->t_last; tile >= units->t_first; --tile) {
+        for (int k = 0; k < P.n_steps; ++k) {
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity); parity ^= 1;
+        }
+      }
+    }
+  } else {
+    const int e = warp - kTcRoleWarps;
+    const int row = 32 * (warp & 3) + lane;
+    const int cq = e >> 2;
+    const int col_base = kTcCols * cq;
+    const int first_chunk = col_base / 16;
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + col_base;
+    const float* b1 = reinterpret_cast<const float*>(smem + TcSmemLayout::b1) + col_base;
+    const float* b2 = reinterpret_cast<const float*>(smem + TcSmemLayout::b2) + col_base;
+    const float* w3 = reinterpret_cast<const float*>(smem + TcSmemLayout::w3) + col_base;
+    float* part = reinterpret_cast<float*>(smem + TcSmemLayout::hmc_part);   // [2][4 kinds][4 cq][128 rows]
+    const uint32_t acc_bar = smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8);
+    const bool with_lo = P.passes == 3;
+    const long long numel = H.n * H.d;
+    const bool quad_rng = (H.d % 4 == 0);
+    const float b3 = P.b3[0];
+    uint32_t parity = 0;
+    auto mass_div = [&](float v, int col) {   // leapfrog.py:167-177
+      if (H.mass.kind == 1) return __fdiv_rn(v, H.mass.safe_scalar);
+      if (H.mass.kind == 2) return __fdiv_rn(v, fmaxf(col < H.d ? H.mass.vec[col] : 1.0f, 1e-10f));
+      return v;
+    };
+    auto kin_term = [&](float pv, int col) {   // hmc.py:148-159 (summand)
+      const float sq = __fmul_rn(pv, pv);
+      return (H.mass.kind == 2) ? __fdiv_rn(sq, col < H.d ? H.mass.vec[col] : 1.0f) : sq;
+    };
+
+    for (int tile = units->t_last; tile >= units->t_first; --tile) {
+      const long long grow = (long long)tile * kTcM + row;
+      const bool rv = grow < H.n;
+      float x[kTcCols];
+#pragma unroll
+      for (int i = 0; i < kTcCols; ++i) {
+        const int col = col_base + i;
+        x[i] = (rv && col < H.d) ? H.x_in[grow * H.d + col] : 0.0f;
+      }
+      store_a_cols(smem, row, col_base, x, with_lo);
+      signal_cols(smem, first_chunk, lane);
+      RngStream rp, ru;
+      rp.k0 = H.rng_p.k0; rp.k1 = H.rng_p.k1; rp.T = H.rng_p.T; rp.mode = H.rng_p.mode; rp.ctr_base = H.rng_p.ctr_base;
+      ru.k0 = H.rng_u.k0; ru.k1 = H.rng_u.k1; ru.T = H.rng_u.T; ru.mode = H.rng_u.mode; ru.ctr_base = H.rng_u.ctr_base;
+      int until_keep = H.thin_start, kept = H.kept_base;
+      float e_final = 0.0f;
+
+      for (int ip = 0; ip < H.n_prop; ++ip) {
+        const float h = tab.h[ip & tab.mask];
+        const float half_h = __fmul_rn(0.5f, h);
+        float* pp = part + (ip & 1) * (4 * 4 * kTcM);
+        float* e0p = pp + (0 * 4 + cq) * kTcM;
+        float* e1p = pp + (1 * 4 + cq) * kTcM;
+        float* k0p = pp + (2 * 4 + cq) * kTcM;
+        float* k1p = pp + (3 * 4 + cq) * kTcM;
+        // park the pre-proposal state, draw the momentum (hmc.py:245 / :92-134) into TMEM, K(p) partial
+        {
+          float ksum = 0.0f;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            float pv[16];
+            const int c0 = col_base + 16 * blk;
+            const long long li0 = grow * H.d + c0;
+            if (H.rng_p.mode == 2 && quad_rng) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint64_t q = (uint64_t)(li0 + 4 * q4) >> 2;
+                const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rp.ctr_base,
+                                              (uint32_t)(rp.ctr_base >> 32), rp.k0, rp.k1);
+                const float4 nn = normal4(w);   // accurate transform: identical to the per-element path of the other HMC kernels
+                pv[4 * q4] = nn.x; pv[4 * q4 + 1] = nn.y; pv[4 * q4 + 2] = nn.z; pv[4 * q4 + 3] = nn.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool in = rv && (c0 + i) < H.d;
+                float ev = 0.0f;
+                if (in) ev = (H.rng_p.mode == 0) ? H.noise_p[(long long)ip * numel + li0 + i] : normal_for_element(rp, (uint64_t)(li0 + i));
+                pv[i] = ev;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c0 + i;
+              const bool in = rv && col < H.d;
+              float v = in ? pv[i] : 0.0f;
+              if (H.mass.kind == 1) v = __fmul_rn(v, H.mass.sqrt_scalar);                       // hmc.py:124
+              else if (H.mass.kind == 2) v = __fmul_rn(v, sqrtf(col < H.d ? H.mass.vec[col] : 1.0f));   // hmc.py:133
+              pv[i] = v;
+              ksum += kin_term(v, col);
+              if (in) H.x_out[grow * H.d + col] = x[16 * blk + i];
+            }
+            tmem_st16(lane_addr + 384 + 16 * blk, pv);
+          }
+          k0p[row] = ksum;
+        }
+        for (int l = 0; l <= L; ++l) {
+          const bool want_e = (l == 0) || (l == L);
+          // E1: z1 -> h1 ; act'(z1) -> TMEM [256, 384)
+          mbar_wait(acc_bar, parity); parity ^= 1;
+          tcgen05_fence_after();
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            float v[16], sd[16];
+            tmem_ld16(lane_addr + 0 + 16 * blk, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) act_fast<ACT>(v[i] + b1[16 * blk + i], v[i], sd[i]);
+            tmem_st16(lane_addr + 256 + 16 * blk, sd);
+            store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+            tcgen05_fence_before();
+            signal_one(smem, first_chunk + blk, lane);
+          }
+          // E2: z2 -> delta2 = w3 * act'(z2) ; energy partial w3 . act(z2)
+          mbar_wait(acc_bar, parity); parity ^= 1;
+          tcgen05_fence_after();
+          float esum = 0.0f;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            float v[16];
+            tmem_ld16(lane_addr + 128 + 16 * blk, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float hh, dh;
+              act_fast<ACT>(v[i] + b2[16 * blk + i], hh, dh);
+              esum = fmaf(w3[16 * blk + i], hh, esum);
+              v[i] = w3[16 * blk + i] * dh;
+            }
+            store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+            tcgen05_fence_before();
+            signal_one(smem, first_chunk + blk, lane);
+          }
+          if (want_e) { if (l == 0) e0p[row] = esum; else e1p[row] = esum; }
+          // E3: t -> delta1 = t * act'(z1)
+          mbar_wait(acc_bar, parity); parity ^= 1;
+          tcgen05_fence_after();
+          tmem_st_wait();
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            float v[16], sd[16];
+            tmem_ld16(lane_addr + 0 + 16 * blk, v);
+            tmem_ld16(lane_addr + 256 + 16 * blk, sd);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= sd[i];
+            store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+            tcgen05_fence_before();
+            signal_one(smem, first_chunk + blk, lane);
+          }
+          // E4: force -> leapfrog kick(s) and drift (leapfrog.py:160-185, safe mode)
+          mbar_wait(acc_bar, parity); parity ^= 1;
+          tcgen05_fence_after();
+          float ksum = 0.0f;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            float g[16], pv[16];
+            tmem_ld16(lane_addr + 128 + 16 * blk, g);
+            tmem_ld16(lane_addr + 384 + 16 * blk, pv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = col_base + 16 * blk + i;
+              const float f = clamp_torch(-g[i], -kSafeClamp, kSafeClamp);
+              float xv = x[16 * blk + i], p_ = pv[i];
+              if (l > 0) {                       // bottom of step l: second half kick, then sanitise
+                p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
+                xv = nan_to_num0(xv);
+                p_ = nan_to_num0(p_);
+              }
+              if (l < L) {                       // top of step l+1: first half kick and drift
+                p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
+                xv = __fadd_rn(xv, mass_div(__fmul_rn(h, p_), col));
+              } else {
+                ksum += kin_term(p_, col);
+              }
+              const bool in = rv && col < H.d;
+              x[16 * blk + i] = in ? xv : 0.0f;
+              pv[i] = in ? p_ : 0.0f;
+            }
+            if (l < L) {
+              tmem_st16(lane_addr + 384 + 16 * blk, pv);
+              store_a_16(smem, row, col_base + 16 * blk, x + 16 * blk, with_lo);
+              tcgen05_fence_before();
+              signal_one(smem, first_chunk + blk, lane);
+            }
+          }
+          if (l == L) k1p[row] = ksum;
+        }
+        // all four column quarters of every row have written their partial sums
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kTcEpiWarps) : "memory");
+        float e0 = b3, e1 = b3, kk0 = 0.0f, kk1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          e0 += pp[(0 * 4 + c) * kTcM + row];
+          e1 += pp[(1 * 4 + c) * kTcM + row];
+          kk0 += pp[(2 * 4 + c) * kTcM + row];
+          kk1 += pp[(3 * 4 + c) * kTcM + row];
+        }
+        kk0 = __fmul_rn(0.5f, kk0); kk1 = __fmul_rn(0.5f, kk1);
+        if (H.mass.kind == 1) { kk0 = __fdiv_rn(kk0, H.mass.scalar); kk1 = __fdiv_rn(kk1, H.mass.scalar); }
+        const float h0 = __fadd_rn(clamp_torch(e0, -1e10f, 1e10f), clamp_torch(kk0, 0.0f, 1e10f));   // hmc.py:247-256
+        const float h1 = __fadd_rn(clamp_torch(e1, -1e10f, 1e10f), clamp_torch(kk1, 0.0f, 1e10f));   // hmc.py:268-275
+        const float dh = clamp_torch(__fsub_rn(h0, h1), -50.0f, 50.0f);
+        float a = expf(dh);
+        a = (a != a) ? a : fminf(a, 1.0f);
+        float u = 0.0f;
+        if (rv) u = (H.rng_u.mode == 0) ? H.noise_u[(long long)ip * H.n + grow] : uniform_for_element(ru, (uint64_t)grow);
+        const bool accepted = u < a;
+        e_final = accepted ? e1 : e0;
+        if (!accepted) {
+#pragma unroll
+          for (int i = 0; i < kTcCols; ++i) {
+            const int col = col_base + i;
+            x[i] = (rv && col < H.d) ? H.x_out[grow * H.d + col] : 0.0f;
+          }
+        }
+        if (H.accept_count && cq == 0) {
+          const unsigned m = __ballot_sync(0xffffffffu, rv && accepted);
+          if (lane == 0 && m) atomicAdd(H.accept_count + H.prop_base + ip, __popc(m));
+        }
+        rp.ctr_base += H.rng_p.ctr_step;
+        ru.ctr_base += H.rng_u.ctr_step;
+        if (H.traj && --until_keep == 0) {
+          until_keep = H.thin;
+          if (kept < H.n_kept && rv) {
+#pragma unroll
+            for (int i = 0; i < kTcCols; ++i)
+              if (col_base + i < H.d) H.traj[(grow * H.n_kept + kept) * H.d + col_base + i] = x[i];
+          }
+          ++kept;
+        }
+        if (ip + 1 < H.n_prop) {   // the selected state is the A operand of the next proposal's first evaluation
+          store_a_cols(smem, row, col_base, x, with_lo);
+          signal_cols(smem, first_chunk, lane);
+        }
+      }
+      if (rv) {
+#pragma unroll
+        for (int i = 0; i < kTcCols; ++i)
+          if (col_base + i < H.d) H.x_out[grow * H.d + col_base + i] = x[i];
+        if (H.energy_out && cq == 0) H.energy_out[grow] = clamp_torch(e_final, -1e10f, 1e10f);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// one chunk of proposals of ebm_hmc_burst_f32 for an MLP energy on the tensor cores (chunk loop: ebm_hmc.cu)
+int hmc_mlp_tc_launch(const EbmEnergyDesc* e, const HmcParams& H, const HStepTable& tab, int passes, cudaStream_t st) {
+  const DeviceInfo& di = device_info(current_device());
+  TcHmcParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.H = H;
+  TcParams& P = Q.T;
+  P.W1 = e->buf[0]; P.b1 = e->buf[1]; P.W2 = e->buf[2]; P.b2 = e->buf[3]; P.w3 = e->buf[4]; P.b3 = e->buf[5];
+  P.d = e->dim; P.h1 = e->hidden1; P.h2 = e->hidden2;
+  P.passes = passes;
+  P.n = H.n;
+  P.n_steps = H.n_prop * (H.n_leapfrog + 1);
+  const long long tiles = (H.n + kTcM - 1) / kTcM;
+  const int sms = (e->sm_margin > 0 && e->sm_margin < di.sm_count) ? di.sm_count - e->sm_margin : di.sm_count;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  mlp_schedule_whole_tiles(P.sched, tiles, P.n_steps, grid);
+#define CALL(A)                                                                                                  \
+  {                                                                                                              \
+    auto kern = hmc_mlp_tc_kernel<A>;                                                                            \
+    EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmemLayout::hmc_total));  \
+    kern<<<grid, kTcThreads, TcSmemLayout::hmc_total, st>>>(Q, tab);                                             \
+  }
+  switch (e->activation) {
+    case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;
+    case EBM_ACT_TANH: CALL(EBM_ACT_TANH); break;
+    case EBM_ACT_RELU: CALL(EBM_ACT_RELU); break;
+    default: CALL(EBM_ACT_SOFTPLUS); break;
+  }
+#undef CALL
+  return launch_status("hmc_mlp_tc_kernel");
+}
+
 int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
   const EbmEnergyDesc* e = c.e;
   if (e->dim > kTcW || e->hidden1 > kTcW || e->hidden2 > kTcW) {
@@ -436,7 +771,7 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
   const long long numel = (long long)c.n * e->dim;
   TcParams P;
   memset(&P, 0, sizeof(P));
-  P.W1 = e->buf[0]; P.b1 = e->buf[1]; P.W2 = e->buf[2]; P.b2 = e->buf[3]; P.w3 = e->buf[4];
+  P.W1 = e->buf[0]; P.b1 = e->buf[1]; P.W2 = e->buf[2]; P.b2 = e->buf[3]; P.w3 = e->buf[4]; P.b3 = e->buf[5];
   P.d = e->dim; P.h1 = e->hidden1; P.h2 = e->hidden2;
   P.passes = passes;
   P.n = c.n;
