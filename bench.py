@@ -543,13 +543,16 @@ def torch_cuda_baseline(dev, workload: str = "c2", k_sample: int = 20):
     en = _oracle_energy(workload, dev)
     olang.sample(en, x0, 3, 0.01, 1.0, generator=gen)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    olang.sample(en, x0, k_sample, 0.01, 1.0, generator=gen)
-    b.record()
-    torch.cuda.synchronize()
-    return {"value": n * k_sample / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
-            "what": "oracle (op-for-op restatement of the reference sampler, autograd gradient) on the same GPU",
+    best = float("inf")
+    for _ in range(3):   # best of three, to be fair to the reference
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        olang.sample(en, x0, k_sample, 0.01, 1.0, generator=gen)
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return {"value": n * k_sample / (best * 1e-3), "unit": UNIT,
+            "what": "oracle (op-for-op restatement of the reference sampler, autograd gradient) on the same GPU, best of 3",
             "sample": f"{n}x{d} chains, {k_sample} steps"}
 
 
@@ -567,15 +570,18 @@ def torch_cuda_hmc_baseline(dev, workload: str):
         en, h = E.make_mlp(128, (128, 128), "silu", seed=0).to(dev), 0.05
     x0 = torch.randn(n_s, d, device=dev)
     gen = torch.Generator(dev).manual_seed(1)
-    ohmc.sample(en, x0, 1, h, L, generator=gen)
+    ohmc.sample(en, x0, 2, h, L, generator=gen)   # warm-up: cuBLAS handles, autograd, allocator
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    ohmc.sample(en, x0, 2, h, L, generator=gen)
-    b.record()
-    torch.cuda.synchronize()
-    return {"value": n_s * 2 * L / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
-            "what": "oracle (op-for-op restatement of the reference HMC sampler) on the same GPU",
+    best = float("inf")
+    for _ in range(3):   # best of three, to be fair to the reference
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ohmc.sample(en, x0, 2, h, L, generator=gen)
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return {"value": n_s * 2 * L / (best * 1e-3), "unit": UNIT,
+            "what": "oracle (op-for-op restatement of the reference HMC sampler) on the same GPU, best of 3",
             "sample": f"{n_s}x{d} chains, 2 proposals of {L} leapfrog steps"}
 
 

@@ -21,6 +21,7 @@
 #include "umma.cuh"
 #include "mlp_schedule.cuh"
 #include <cuda_bf16.h>
+#include <type_traits>
 
 namespace ebm {
 
@@ -440,6 +441,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
 // barrier per proposal) and every thread takes the Metropolis decision of its row.  The pre-proposal state is parked
 // in x_out.  Deviation from the reference in one corner: when safe-mode sanitising rewrites a NaN/inf coordinate the
 // reference recomputes the force at the sanitised state before the next step; here the carried force is kept.
+// a thread's 32 consecutive columns of one row <-> global memory: eight 128-bit accesses when the row is 16-byte aligned
+// and lies inside the state, scalar otherwise
+__device__ __forceinline__ void tc_store_row32(float* __restrict__ dst, long long grow, int d, int col_base, bool rv,
+                                               const float (&x)[kTcCols]) {
+  if (!rv) return;
+  float* p = dst + grow * d + col_base;
+  if (col_base + kTcCols <= d && (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < kTcCols / 4; ++j)
+      reinterpret_cast<float4*>(p)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTcCols; ++i)
+      if (col_base + i < d) p[i] = x[i];
+  }
+}
+__device__ __forceinline__ void tc_load_row32(const float* __restrict__ src, long long grow, int d, int col_base, bool rv,
+                                              float (&x)[kTcCols]) {
+  const float* p = src + grow * d + col_base;
+  if (rv && col_base + kTcCols <= d && (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < kTcCols / 4; ++j) {
+      const float4 t = reinterpret_cast<const float4*>(p)[j];
+      x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTcCols; ++i) x[i] = (rv && col_base + i < d) ? p[i] : 0.0f;
+  }
+}
+
+// out-of-line copy of the per-element draw: inlined 32 times (64-bit division + Philox + accurate Box-Muller each) it
+// made the kernel 370 KB of code and the epilogue loop stall on instruction fetch (ncu: 14 % no_instruction)
+__device__ __noinline__ float normal_for_element_call(uint32_t k0, uint32_t k1, unsigned long long ctr_base,
+                                                       unsigned long long T, int mode, unsigned long long li) {
+  RngStream rs;
+  rs.k0 = k0; rs.k1 = k1; rs.ctr_base = ctr_base; rs.T = T; rs.mode = mode;
+  return normal_for_element(rs, li);
+}
+
 struct TcHmcParams {
   TcParams T;      // weights, widths, passes, schedule; T.n_steps = proposals of this launch * (L + 1)
   HmcParams H;
@@ -514,11 +555,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
       const long long grow = (long long)tile * kTcM + row;
       const bool rv = grow < H.n;
       float x[kTcCols];
-#pragma unroll
-      for (int i = 0; i < kTcCols; ++i) {
-        const int col = col_base + i;
-        x[i] = (rv && col < H.d) ? H.x_in[grow * H.d + col] : 0.0f;
-      }
+      tc_load_row32(H.x_in, grow, H.d, col_base, rv, x);
       store_a_cols(smem, row, col_base, x, with_lo);
       signal_cols(smem, first_chunk, lane);
       RngStream rp, ru;
@@ -537,6 +574,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
         float* k1p = pp + (3 * 4 + cq) * kTcM;
         // park the pre-proposal state, draw the momentum (hmc.py:245 / :92-134) into TMEM, K(p) partial
         {
+          tc_store_row32(H.x_out, grow, H.d, col_base, rv, x);
           float ksum = 0.0f;
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
@@ -557,7 +595,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
               for (int i = 0; i < 16; ++i) {
                 const bool in = rv && (c0 + i) < H.d;
                 float ev = 0.0f;
-                if (in) ev = (H.rng_p.mode == 0) ? H.noise_p[(long long)ip * numel + li0 + i] : normal_for_element(rp, (uint64_t)(li0 + i));
+                if (in) ev = (H.rng_p.mode == 0) ? H.noise_p[(long long)ip * numel + li0 + i]
+                                                 : normal_for_element_call(rp.k0, rp.k1, rp.ctr_base, rp.T, rp.mode, (uint64_t)(li0 + i));
                 pv[i] = ev;
               }
             }
@@ -570,7 +609,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
               else if (H.mass.kind == 2) v = __fmul_rn(v, sqrtf(col < H.d ? H.mass.vec[col] : 1.0f));   // hmc.py:133
               pv[i] = v;
               ksum += kin_term(v, col);
-              if (in) H.x_out[grow * H.d + col] = x[16 * blk + i];
             }
             tmem_st16(lane_addr + 384 + 16 * blk, pv);
           }
@@ -631,38 +669,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
           mbar_wait(acc_bar, parity); parity ^= 1;
           tcgen05_fence_after();
           float ksum = 0.0f;
+          // three straight-line variants: first evaluation (top of step 1), middle (bottom of step l + top of step l+1),
+          // last (bottom of step L + kinetic energy) -- `l` is uniform, so this only removes per-element predication
+          auto e4 = [&](auto first_c, auto last_c) {
+            constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
 #pragma unroll
-          for (int blk = 0; blk < 2; ++blk) {
-            float g[16], pv[16];
-            tmem_ld16(lane_addr + 128 + 16 * blk, g);
-            tmem_ld16(lane_addr + 384 + 16 * blk, pv);
+            for (int blk = 0; blk < 2; ++blk) {
+              float g[16], pv[16];
+              tmem_ld16(lane_addr + 128 + 16 * blk, g);
+              tmem_ld16(lane_addr + 384 + 16 * blk, pv);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int col = col_base + 16 * blk + i;
-              const float f = clamp_torch(-g[i], -kSafeClamp, kSafeClamp);
-              float xv = x[16 * blk + i], p_ = pv[i];
-              if (l > 0) {                       // bottom of step l: second half kick, then sanitise
-                p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
-                xv = nan_to_num0(xv);
-                p_ = nan_to_num0(p_);
+              for (int i = 0; i < 16; ++i) {
+                const int col = col_base + 16 * blk + i;
+                const float f = clamp_torch(-g[i], -kSafeClamp, kSafeClamp);
+                float xv = x[16 * blk + i], p_ = pv[i];
+                if (!kFirst) {                     // bottom of step l: second half kick, then sanitise
+                  p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
+                  xv = nan_to_num0(xv);
+                  p_ = nan_to_num0(p_);
+                }
+                if (!kLast) {                      // top of step l+1: first half kick and drift
+                  p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
+                  xv = __fadd_rn(xv, mass_div(__fmul_rn(h, p_), col));
+                } else {
+                  ksum += kin_term(p_, col);
+                }
+                const bool in = rv && col < H.d;
+                x[16 * blk + i] = in ? xv : 0.0f;
+                pv[i] = in ? p_ : 0.0f;
               }
-              if (l < L) {                       // top of step l+1: first half kick and drift
-                p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
-                xv = __fadd_rn(xv, mass_div(__fmul_rn(h, p_), col));
-              } else {
-                ksum += kin_term(p_, col);
+              if (!kLast) {
+                tmem_st16(lane_addr + 384 + 16 * blk, pv);
+                store_a_16(smem, row, col_base + 16 * blk, x + 16 * blk, with_lo);
+                tcgen05_fence_before();
+                signal_one(smem, first_chunk + blk, lane);
               }
-              const bool in = rv && col < H.d;
-              x[16 * blk + i] = in ? xv : 0.0f;
-              pv[i] = in ? p_ : 0.0f;
             }
-            if (l < L) {
-              tmem_st16(lane_addr + 384 + 16 * blk, pv);
-              store_a_16(smem, row, col_base + 16 * blk, x + 16 * blk, with_lo);
-              tcgen05_fence_before();
-              signal_one(smem, first_chunk + blk, lane);
-            }
-          }
+          };
+          if (l == 0) e4(std::true_type{}, std::false_type{});
+          else if (l < L) e4(std::false_type{}, std::false_type{});
+          else e4(std::false_type{}, std::true_type{});
           if (l == L) k1p[row] = ksum;
         }
         // all four column quarters of every row have written their partial sums
@@ -686,13 +732,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
         if (rv) u = (H.rng_u.mode == 0) ? H.noise_u[(long long)ip * H.n + grow] : uniform_for_element(ru, (uint64_t)grow);
         const bool accepted = u < a;
         e_final = accepted ? e1 : e0;
-        if (!accepted) {
-#pragma unroll
-          for (int i = 0; i < kTcCols; ++i) {
-            const int col = col_base + i;
-            x[i] = (rv && col < H.d) ? H.x_out[grow * H.d + col] : 0.0f;
-          }
-        }
+        if (!accepted) tc_load_row32(H.x_out, grow, H.d, col_base, rv, x);
         if (H.accept_count && cq == 0) {
           const unsigned m = __ballot_sync(0xffffffffu, rv && accepted);
           if (lane == 0 && m) atomicAdd(H.accept_count + H.prop_base + ip, __popc(m));
@@ -713,12 +753,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
           signal_cols(smem, first_chunk, lane);
         }
       }
-      if (rv) {
-#pragma unroll
-        for (int i = 0; i < kTcCols; ++i)
-          if (col_base + i < H.d) H.x_out[grow * H.d + col_base + i] = x[i];
-        if (H.energy_out && cq == 0) H.energy_out[grow] = clamp_torch(e_final, -1e10f, 1e10f);
-      }
+      tc_store_row32(H.x_out, grow, H.d, col_base, rv, x);
+      if (rv && H.energy_out && cq == 0) H.energy_out[grow] = clamp_torch(e_final, -1e10f, 1e10f);
     }
   }
   tcgen05_fence_before();
