@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
             for (int i = 0; i < 16; ++i) {
               const bool in = rv && (c0 + i) < P.d;
               float ev = 0.0f;
-              if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i] : normal_for_element(rs, (uint64_t)(li0 + i));
+              if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i]
+                                             : normal_for_element_call(rs.k0, rs.k1, rs.ctr_base, rs.T, rs.mode, (uint64_t)(li0 + i));
               eps[i] = ev;
             }
           }
@@ -470,15 +471,6 @@ __device__ __forceinline__ void tc_load_row32(const float* __restrict__ src, lon
 #pragma unroll
     for (int i = 0; i < kTcCols; ++i) x[i] = (rv && col_base + i < d) ? p[i] : 0.0f;
   }
-}
-
-// out-of-line copy of the per-element draw: inlined 32 times (64-bit division + Philox + accurate Box-Muller each) it
-// made the kernel 370 KB of code and the epilogue loop stall on instruction fetch (ncu: 14 % no_instruction)
-__device__ __noinline__ float normal_for_element_call(uint32_t k0, uint32_t k1, unsigned long long ctr_base,
-                                                       unsigned long long T, int mode, unsigned long long li) {
-  RngStream rs;
-  rs.k0 = k0; rs.k1 = k1; rs.ctr_base = ctr_base; rs.T = T; rs.mode = mode;
-  return normal_for_element(rs, li);
 }
 
 struct TcHmcParams {

@@ -561,9 +561,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
                   if (P.rng.mode == 0) {
                     ev = P.noise[(long long)k * (P.n * P.d) + li0 + i];
                   } else {
-                    RngStream rs;
-                    rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode; rs.ctr_base = ctr_base;
-                    ev = normal_for_element(rs, (uint64_t)(li0 + i));
+                    ev = normal_for_element_call(P.rng.k0, P.rng.k1, ctr_base, P.rng.T, P.rng.mode, (uint64_t)(li0 + i));
                   }
                 }
                 eps[i] = ev;
