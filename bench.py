@@ -49,8 +49,16 @@ WORKLOADS = {
            "NCCL all-gather of the negatives at burst end", 65536, 784, 20),
 }
 WEAK = {"c5"}
+SM_MARGIN = None   # --sm-margin
 METRIC = "langevin_chain_steps_per_sec"
 UNIT = "chain-steps/s"
+
+
+def c5_uses_dma(world: int) -> bool:
+    """C5 gather policy (measured): peer-to-peer DMA pushes move ~240 GB/s per GPU and take no SM, so
+    they hide under the 3.2 ms burst while (world - 1) * 205 MB fits (world <= 4); at 8 GPUs (1.44 GB per GPU per burst)
+    NCCL's SM-driven all-gather on 32 SMs left free by the burst is faster (4.67 ms vs 6.14 ms per step)."""
+    return world <= 4
 
 
 def measured_peaks():
@@ -254,7 +262,9 @@ def make_workload(name: str, n_local: int, dev):
         model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev)
         sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=dev, rng="native")
         if name in WEAK and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            model.sm_margin = 1  # the burst-end gather of burst i runs next to burst i+1: leave it an SM for its barrier kernel
+            # the burst-end gather of burst i runs next to burst i+1: leave it SMs (1 for the barrier kernel of the DMA
+            # gather; NCCL's channels need more)
+            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else (1 if c5_uses_dma(int(os.environ.get("WORLD_SIZE", "1"))) else 32)
         cd = te.ContrastiveDivergence(model, sampler, k_steps=k, persistent=True, buffer_size=n_local, init_steps=0,
                                       new_sample_ratio=0.0, device=dev)
         gen = torch.Generator(dev).manual_seed(1234)
@@ -303,7 +313,8 @@ def run_ours(args):
     # C2 at N > 1: the burst kernel stores its shard straight into every rank's gathered tensor (symmetric memory, NVLink
     # peer stores) and a device-side barrier replaces the NCCL all-gather; NCCL stays the fallback if peer mapping fails
     peer = None
-    if world > 1 and args.workload in ("c2", "c5") and not args.nccl_gather:
+    want_peer = args.workload == "c2" or (args.workload == "c5" and c5_uses_dma(world))
+    if world > 1 and want_peer and not args.nccl_gather:
         ok = torch.ones(1, device=dev)
         try:
             from torchebm_b200.distributed import PeerGatherBuffer
@@ -630,9 +641,12 @@ def main():
     ap.add_argument("--cpu-k", type=int, default=5, help="Langevin steps per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: use the NCCL all-gather instead of fused peer stores")
+    ap.add_argument("--sm-margin", type=int, default=None, help="c5, N > 1: SMs the persistent burst leaves to the gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    global SM_MARGIN
+    SM_MARGIN = args.sm_margin
     if args.impl == "reference":
         run_reference(args)
     else:

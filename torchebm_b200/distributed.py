@@ -108,6 +108,8 @@ class PeerGatherBuffer:
         if n_total % self.world != 0:
             raise ValueError(f"n_total ({n_total}) must be divisible by the world size ({self.world})")
         self.rows_per_rank = n_total // self.world
+        self._push_streams = None
+        self._peer_views = None
 
     def barrier(self) -> None:
         self.handle.barrier(channel=0)
@@ -120,9 +122,23 @@ class PeerGatherBuffer:
             raise ValueError("every rank must hold n_total / world chains")
         lo = self.rank * self.rows_per_rank
         shape, dtype = tuple(self.tensor.shape), self.tensor.dtype
+        cur = torch.cuda.current_stream(self.tensor.device)
+        if self._push_streams is None:
+            # one stream per destination: the copies then run on different copy engines at the same time (a single
+            # engine moves ~200 GB/s; NVLink carries several times that)
+            self._push_streams = [torch.cuda.Stream(device=self.tensor.device) for _ in range(self.world)]
+            self._peer_views = [self.tensor if w == self.rank else self.handle.get_buffer(w, shape, dtype)
+                                for w in range(self.world)]
+        ready = torch.cuda.Event()
+        ready.record(cur)
         for w in range(self.world):
-            dst = self.tensor if w == self.rank else self.handle.get_buffer(w, shape, dtype)
-            dst[lo:lo + self.rows_per_rank].copy_(x_local, non_blocking=True)
+            st = self._push_streams[w]
+            st.wait_event(ready)
+            x_local.record_stream(st)
+            with torch.cuda.stream(st):
+                self._peer_views[w][lo:lo + self.rows_per_rank].copy_(x_local, non_blocking=True)
+        for st in self._push_streams:
+            cur.wait_stream(st)
         self.barrier()
 
     def burst(self, desc, x_local: torch.Tensor, n_steps: int, step_sizes, noise_scales, **kw) -> torch.Tensor:
