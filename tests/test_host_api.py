@@ -16,7 +16,7 @@ def test_sample_signature_matches_reference_contract():
     # tests/samplers/test_api_contract.py:27-46,145-187 of the reference
     prefix = ["self", "x", "dim", "n_steps", "n_samples", "thin", "return_trajectory", "return_diagnostics",
               "reset_schedulers"]
-    for cls in (te.LangevinDynamics, te.HamiltonianMonteCarlo):
+    for cls in (te.LangevinDynamics, te.HamiltonianMonteCarlo, te.GradientDescentSampler, te.NesterovSampler):
         sig = inspect.signature(cls.sample)
         names = list(sig.parameters)
         assert names[:len(prefix)] == prefix
@@ -26,7 +26,9 @@ def test_sample_signature_matches_reference_contract():
         assert sig.parameters["model_kwargs"].kind is inspect.Parameter.KEYWORD_ONLY
         assert not any(p.kind in (p.VAR_POSITIONAL, p.VAR_KEYWORD) for p in sig.parameters.values())
         ctor = list(inspect.signature(cls.__init__).parameters)
-        assert ctor[1] == "model" and ctor.index("dtype") < ctor.index("device") < ctor.index("integrator")
+        assert ctor[1] == "model" and ctor.index("dtype") < ctor.index("device")
+        if "integrator" in ctor:
+            assert ctor.index("device") < ctor.index("integrator")
 
 
 def test_constructor_validation():
@@ -51,6 +53,15 @@ def test_cpu_sampler_raises_loudly():
     s = te.LangevinDynamics(te.DoubleWellModel(), step_size=0.01)
     with pytest.raises(RuntimeError, match="CUDA device only"):
         s.sample(dim=2, n_steps=2)
+    for other in (te.GradientDescentSampler(te.DoubleWellModel(), step_size=0.01),
+                  te.NesterovSampler(te.DoubleWellModel(), step_size=0.01, momentum=0.5),
+                  te.HamiltonianMonteCarlo(te.DoubleWellModel(), step_size=0.01)):
+        with pytest.raises(RuntimeError, match="CUDA device only"):
+            other.sample(dim=2, n_steps=2)
+    with pytest.raises(ValueError, match="momentum must be in"):
+        te.NesterovSampler(te.DoubleWellModel(), momentum=1.5)
+    # the persistent-CD one-call path declines (None) instead of touching a CPU buffer
+    assert s.sample_from_buffer(torch.zeros(4, 2), torch.zeros(4, dtype=torch.long), 0, 3) is None
     with pytest.raises(ValueError, match="thin must be >= 1"):
         s.sample(dim=2, thin=0)
 
