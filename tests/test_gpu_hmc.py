@@ -297,3 +297,32 @@ def test_hmc_fused_mlp_kernel_matches_oracle(act, mass_kind, precision):
     assert bad < 0.01, bad
     torch.testing.assert_close(diag["acceptance_rate"], wd["acceptance_rate"], atol=0.01, rtol=0)
     torch.testing.assert_close(diag["energy"], wd["energy"], atol=1e-2, rtol=1e-3)
+
+
+def test_hmc_tc_balanced_proposal_split_is_bit_identical():
+    """With a workspace the tensor-core HMC kernel hands every CTA an equal range of (tile, proposal) pairs, so a tile's
+    proposals may be split between two SMs (only the chain state crosses the split); without one every tile runs whole.
+    Counter-based draws => identical chains, acceptance counts, energies and trajectories."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    torch.manual_seed(1)
+    n, d, L, k = 128 * 190 + 9, 32, 3, 7    # 191 tiles on 148 SMs
+    mlp = te.MLPEnergy(dim=d, hidden=(64, 48), activation="silu").to(DEV)
+    x0 = torch.randn(n, d, device=DEV)
+    outs = []
+    for with_ws in (True, False):
+        desc = te.energy_descriptor(mlp, d, x0.device)
+        assert desc.c.buf[6]
+        if not with_ws:
+            desc.c.buf[6] = None
+        acc = torch.zeros(k, dtype=torch.int32, device=DEV)
+        e_out = torch.empty(n, device=DEV)
+        traj = torch.empty(n, k // 2, d, device=DEV)
+        out = ops.hmc_burst(desc, x0, k, L, [0.05], rng_mode=_lib.RNG_TORCH, seed=11, offset=8, traj=traj, thin=2,
+                            accept_count=acc, energy_out=e_out)
+        outs.append((out, acc, e_out, traj))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    acc = outs[0][1]
+    assert bool((acc <= n).all()) and int(acc.sum()) > 0.3 * n * k

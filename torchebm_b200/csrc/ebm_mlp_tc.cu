@@ -493,7 +493,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
     mbar_init(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8), 1);
     fence_mbar_init();
   }
-  if (threadIdx.x == 32) mlp_units_compute(P.sched, P.n_steps, reinterpret_cast<volatile MlpUnits*>(smem + TcSmemLayout::units));
+  // work quantum = one proposal of one tile: a tile's proposals may be split between two CTAs (mlp_schedule.cuh); only
+  // the chain state crosses the split (momentum, energy and force are rebuilt at the top of every proposal)
+  if (threadIdx.x == 32) mlp_units_compute(P.sched, H.n_prop, reinterpret_cast<volatile MlpUnits*>(smem + TcSmemLayout::units));
   if (warp == 0) tmem_alloc(smem_u32(smem + TcSmemLayout::tmem_slot), 512);
   fence_proxy_async();
   tcgen05_fence_before();
@@ -508,7 +510,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
     if (warp == 0 && lane == 0) {
       uint32_t parity = 0;
       for (int tile = units->t_last; tile >= units->t_first; --tile) {
-        for (int k = 0; k < P.n_steps; ++k) {
+        const int n_evals = (mlp_unit_s1(units, tile, H.n_prop) - mlp_unit_s0(units, tile)) * (L + 1);
+        for (int k = 0; k < n_evals; ++k) {
           tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity); parity ^= 1;
           tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity); parity ^= 1;
           tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity); parity ^= 1;
@@ -546,17 +549,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
     for (int tile = units->t_last; tile >= units->t_first; --tile) {
       const long long grow = (long long)tile * kTcM + row;
       const bool rv = grow < H.n;
+      const int s0 = mlp_unit_s0(units, tile), s1 = mlp_unit_s1(units, tile, H.n_prop);
+      if (s0 > 0) mlp_unit_acquire(P.sched, kTcEpiWarps);   // earlier proposals of this tile ran on another CTA
       float x[kTcCols];
-      tc_load_row32(H.x_in, grow, H.d, col_base, rv, x);
+      tc_load_row32(s0 == 0 ? H.x_in : H.x_out, grow, H.d, col_base, rv, x);
       store_a_cols(smem, row, col_base, x, with_lo);
       signal_cols(smem, first_chunk, lane);
       RngStream rp, ru;
-      rp.k0 = H.rng_p.k0; rp.k1 = H.rng_p.k1; rp.T = H.rng_p.T; rp.mode = H.rng_p.mode; rp.ctr_base = H.rng_p.ctr_base;
-      ru.k0 = H.rng_u.k0; ru.k1 = H.rng_u.k1; ru.T = H.rng_u.T; ru.mode = H.rng_u.mode; ru.ctr_base = H.rng_u.ctr_base;
-      int until_keep = H.thin_start, kept = H.kept_base;
+      rp.k0 = H.rng_p.k0; rp.k1 = H.rng_p.k1; rp.T = H.rng_p.T; rp.mode = H.rng_p.mode;
+      rp.ctr_base = H.rng_p.ctr_base + (unsigned long long)s0 * H.rng_p.ctr_step;
+      ru.k0 = H.rng_u.k0; ru.k1 = H.rng_u.k1; ru.T = H.rng_u.T; ru.mode = H.rng_u.mode;
+      ru.ctr_base = H.rng_u.ctr_base + (unsigned long long)s0 * H.rng_u.ctr_step;
+      int until_keep = H.thin_start - s0, kept = H.kept_base;
+      if (until_keep <= 0) {   // thin_start / kept_base describe proposal 0 of this launch
+        const int passed = (-until_keep) / H.thin + 1;
+        kept += passed;
+        until_keep += passed * H.thin;
+      }
       float e_final = 0.0f;
 
-      for (int ip = 0; ip < H.n_prop; ++ip) {
+      for (int ip = s0; ip < s1; ++ip) {
         const float h = tab.h[ip & tab.mask];
         const float half_h = __fmul_rn(0.5f, h);
         float* pp = part + (ip & 1) * (4 * 4 * kTcM);
@@ -740,13 +752,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
           }
           ++kept;
         }
-        if (ip + 1 < H.n_prop) {   // the selected state is the A operand of the next proposal's first evaluation
+        if (ip + 1 < s1) {   // the selected state is the A operand of the next proposal's first evaluation
           store_a_cols(smem, row, col_base, x, with_lo);
           signal_cols(smem, first_chunk, lane);
         }
       }
       tc_store_row32(H.x_out, grow, H.d, col_base, rv, x);
-      if (rv && H.energy_out && cq == 0) H.energy_out[grow] = clamp_torch(e_final, -1e10f, 1e10f);
+      if (rv && H.energy_out && cq == 0 && s1 == H.n_prop) H.energy_out[grow] = clamp_torch(e_final, -1e10f, 1e10f);
+      if (s1 < H.n_prop) mlp_unit_release(P.sched);   // the rest of this tile's proposals run on the next CTA
     }
   }
   tcgen05_fence_before();
@@ -772,7 +785,13 @@ int hmc_mlp_tc_launch(const EbmEnergyDesc* e, const HmcParams& H, const HStepTab
   const long long tiles = (H.n + kTcM - 1) / kTcM;
   const int sms = (e->sm_margin > 0 && e->sm_margin < di.sm_count) ? di.sm_count - e->sm_margin : di.sm_count;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  mlp_schedule_whole_tiles(P.sched, tiles, P.n_steps, grid);
+  int* flags = reinterpret_cast<int*>(const_cast<float*>(e->buf[6]));  // NULL: whole tiles per CTA
+  if (flags) {
+    int rc0 = mlp_schedule_setup(P.sched, tiles, H.n_prop, grid, flags, st);
+    if (rc0) return rc0;
+  } else {
+    mlp_schedule_whole_tiles(P.sched, tiles, H.n_prop, grid);
+  }
 #define CALL(A)                                                                                                  \
   {                                                                                                              \
     auto kern = hmc_mlp_tc_kernel<A>;                                                                            \
