@@ -125,6 +125,15 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
                            uint64_t seed, uint64_t offset, const float* noise, float* traj, int32_t thin,
                            void* stream);
 
+/* Same burst with the Heun (improved Euler) SDE scheme: LangevinDynamics(integrator="heun"), i.e. the generic
+ * Runge-Kutta path of core/base_integrator.py:300-347,387-397,673-731 with the tableau of integrators/heun.py
+ * (two gradient evaluations per step, same additive noise and generator consumption as Euler-Maruyama).  Fused for
+ * the elementwise energies; other energies return EBM_ERR_UNSUPPORTED. */
+int ebm_langevin_heun_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                                const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                const float* noise, float* traj, int32_t thin, void* stream);
+
 /* Noise-free descent burst; replaces the loops of GradientDescentSampler.sample (x <- x - eta * grad E(x),
  * samplers/gradient_descent.py:123-138) and NesterovSampler.sample (lookahead gradient + momentum, :258-276) for the
  * elementwise energies (others: EBM_ERR_UNSUPPORTED).  momentum < 0 selects plain gradient descent, 0 <= momentum < 1

@@ -40,6 +40,18 @@ def em_step(x, grad, h: float, ns: float, eps):
     return x1 + (2.0 * (ns**2)) ** 0.5 * dw
 
 
+def heun_step(x, grad_fn, h: float, ns: float, eps):
+    """One reference Heun (improved Euler) SDE step: `LangevinDynamics(integrator="heun")`, i.e. the generic RK path of
+    core/base_integrator.py:300-347,387-397,673-731 with the tableau of integrators/heun.py (a = ((), (1,)),
+    b = (1/2, 1/2)): k1 = f(x); k2 = f(x + h * (1 * k1)); x1 = x + h * (k1/2 + k2/2); then the additive noise of the EM
+    step.  The einsum scalings by 1 and 1/2 are exact, so only the sums and products below round."""
+    k1 = -grad_fn(x)
+    k2 = -grad_fn(x + h * k1)
+    x1 = x + h * (0.5 * k1 + 0.5 * k2)
+    dw = eps * (h**0.5)
+    return x1 + (2.0 * (ns**2)) ** 0.5 * dw
+
+
 @torch.no_grad()
 def sample(
     energy: Energy,
@@ -55,6 +67,7 @@ def sample(
     noise: Optional[torch.Tensor] = None,
     generator: Optional[torch.Generator] = None,
     closed_form: bool = False,
+    scheme: str = "euler_maruyama",
 ):
     """`noise` is `[n_steps, *x.shape]` (injected) or None (draw `randn_like` per step with
     `generator`, the reference's own draw order: SURVEY.md section 8c)."""
@@ -75,9 +88,9 @@ def sample(
     keep = 0
     grad_fn = energy.gradient_closed if closed_form else energy.gradient
     for i in range(n_steps):
-        g = grad_fn(x)
+        g = grad_fn(x) if scheme == "euler_maruyama" else None
         eps = noise[i] if noise is not None else torch.randn_like(x, generator=generator)
-        x = em_step(x, g, hs[i], sigmas[i], eps)
+        x = em_step(x, g, hs[i], sigmas[i], eps) if scheme == "euler_maruyama" else heun_step(x, grad_fn, hs[i], sigmas[i], eps)
         if clamp is not None:
             x = x.clamp_(*clamp)
         if (i + 1) % thin == 0:

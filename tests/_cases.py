@@ -119,3 +119,12 @@ def descent_setup(name, g):
     if name == "nesterov_harmonic_traj":
         kw = dict(thin=2, return_trajectory=True, return_diagnostics=True)
     return en, hs, mu, kw
+
+# Heun SDE integrator behind LangevinDynamics: (golden, oracle energy, sample kwargs)
+HEUN_CASES = ["heun_doublewell", "heun_rastrigin_traj"]
+
+
+def heun_setup(name):
+    if name == "heun_doublewell":
+        return E.DoubleWell(2.0, 1.0), {}
+    return E.Rastrigin(10.0), dict(thin=3, return_trajectory=True)

@@ -265,6 +265,17 @@ def main():
         extra[f"b{i}"] = l.bias.detach()
     langevin_case("langevin_mlp_d784", m, 40, 784, 4, 0.01, 1.0, 21, extra=extra)
 
+    # Heun SDE integrator behind LangevinDynamics: own sampler construction, same case recorder
+    def heun_case(name, model, n, d, k, h, ns, seed, **kw):
+        x0 = torch.randn(n, d, generator=torch.Generator().manual_seed(seed + 1000))
+        noise = predraw_langevin(x0, k, seed)
+        s = LangevinDynamics(model, step_size=h, noise_scale=ns, integrator="heun")
+        res = s.sample(x=x0, n_steps=k, generator=torch.Generator().manual_seed(seed), **kw)
+        save(name, x0=x0, noise=noise, k=k, h=h, ns=ns, out=res)
+
+    heun_case("heun_doublewell", DoubleWellModel(2.0, 1.0), 64, 16, 15, 0.01, 1.0, 41)
+    heun_case("heun_rastrigin_traj", RastriginModel(10.0), 33, 7, 12, 0.002, 0.5, 42, thin=3, return_trajectory=True)
+
     # noise-free descent samplers (samplers/gradient_descent.py); deterministic, so only x0 and the outputs are stored
     from torchebm.samplers import GradientDescentSampler, NesterovSampler
 

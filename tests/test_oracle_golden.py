@@ -165,3 +165,15 @@ def test_descent_oracle_matches_reference_golden(name):
         res2 = odesc.sample(en, g["x0"], int(g["k"]), hs, mu, closed_form=True, **kw)
         out2 = res2[0] if isinstance(res2, tuple) else res2
         assert torch.equal(out2, g["out"])
+
+
+@pytest.mark.parametrize("name", C.HEUN_CASES)
+def test_heun_oracle_matches_reference_golden(name):
+    """`LangevinDynamics(integrator="heun")` restatement vs the unmodified reference, injected noise: bit-exact with the
+    autograd gradient and with the closed forms."""
+    g = C.load(name)
+    en, kw = C.heun_setup(name)
+    for closed in (False, True):
+        out = olang.sample(en, g["x0"], int(g["k"]), float(g["h"]), float(g["ns"]), noise=g["noise"], scheme="heun",
+                           closed_form=closed, **kw)
+        assert torch.equal(out, g["out"])

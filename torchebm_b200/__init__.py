@@ -8,14 +8,14 @@ from . import _lib
 from .core import (BaseModel, BaseScheduler, ConstantScheduler, CosineScheduler, DoubleWellModel,
                    ExponentialDecayScheduler, GaussianModel, HarmonicModel, LinearScheduler, MixtureOfGaussiansModel,
                    MLPEnergy, RastriginModel, energy_descriptor, mark_mlp_energy)
-from .integrators import EulerMaruyamaIntegrator, LeapfrogIntegrator, energy_drift
+from .integrators import EulerMaruyamaIntegrator, HeunIntegrator, LeapfrogIntegrator, energy_drift
 from .losses import BaseContrastiveDivergence, ContrastiveDivergence
 from .samplers import BaseSampler, GradientDescentSampler, HamiltonianMonteCarlo, LangevinDynamics, NesterovSampler
 
 __all__ = [
     "BaseModel", "BaseScheduler", "ConstantScheduler", "CosineScheduler", "DoubleWellModel", "ExponentialDecayScheduler",
     "GaussianModel", "HarmonicModel", "LinearScheduler", "MixtureOfGaussiansModel", "MLPEnergy", "RastriginModel",
-    "energy_descriptor", "mark_mlp_energy", "EulerMaruyamaIntegrator", "LeapfrogIntegrator", "energy_drift",
+    "energy_descriptor", "mark_mlp_energy", "EulerMaruyamaIntegrator", "HeunIntegrator", "LeapfrogIntegrator", "energy_drift",
     "BaseContrastiveDivergence", "ContrastiveDivergence", "BaseSampler", "HamiltonianMonteCarlo", "LangevinDynamics",
     "GradientDescentSampler", "NesterovSampler",
 ]

@@ -164,6 +164,7 @@ struct LangevinCall {
   float* const* peers;
   int n_peers;
   long long peer_row_offset;
+  int scheme;   // 0 = Euler-Maruyama, 1 = Heun (elementwise energies only)
 };
 
 inline int row_grid(const DeviceInfo& di, long long n, int G, int ctas_per_sm) {

@@ -134,6 +134,7 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
   P.has_clamp = c.clamp != nullptr;
   if (c.clamp) { P.clamp_lo = c.clamp[0]; P.clamp_hi = c.clamp[1]; }
   P.traj = c.traj;
+  if (c.scheme == 1 && !c.clamp) { P.clamp_lo = -INFINITY; P.clamp_hi = INFINITY; }   // the Heun kernel always clamps
   if (c.rng_mode == EBM_RNG_TORCH) {
     P.T = torch_threads(di, numel);
     const unsigned long long J = (((unsigned long long)numel + P.T - 1) / P.T + 3) / 4;
@@ -186,9 +187,18 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     if (c.clamp) langevin_elem_kernel<ElemE, RNG, false, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);  \
     else         langevin_elem_kernel<ElemE, RNG, false, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab); \
   }
-    if (c.rng_mode == EBM_RNG_INJECTED) { LAUNCH(0) }
+#define LAUNCH_HEUN(RNG)                                                                                     \
+  if (c.traj) langevin_elem_kernel<ElemE, RNG, true, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);     \
+  else        langevin_elem_kernel<ElemE, RNG, false, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);
+    if (c.scheme == 1) {
+      if (c.rng_mode == EBM_RNG_INJECTED) { LAUNCH_HEUN(0) }
+      else if (c.rng_mode == EBM_RNG_TORCH) { LAUNCH_HEUN(1) }
+      else { LAUNCH_HEUN(2) }
+    }
+    else if (c.rng_mode == EBM_RNG_INJECTED) { LAUNCH(0) }
     else if (c.rng_mode == EBM_RNG_TORCH) { LAUNCH(1) }
     else { LAUNCH(2) }
+#undef LAUNCH_HEUN
 #undef LAUNCH
     int rc = launch_status("langevin_elem_kernel");
     if (rc) return rc;
@@ -260,6 +270,11 @@ static int launch_langevin_row(const RowE& en, const LangevinCall& c) {
 int langevin_mlp_dispatch(const LangevinCall& c);  // ebm_mlp.cu
 
 static int langevin_dispatch(const LangevinCall& c) {
+  if (c.scheme == 1 && c.e->kind != EBM_ENERGY_DOUBLE_WELL && c.e->kind != EBM_ENERGY_HARMONIC &&
+      c.e->kind != EBM_ENERGY_RASTRIGIN) {
+    set_error("the Heun burst is fused for the elementwise energies only (kind %d)", c.e->kind);
+    return EBM_ERR_UNSUPPORTED;
+  }
   switch (c.e->kind) {
     case EBM_ENERGY_DOUBLE_WELL: return launch_langevin_elem(make_dw(c.e), c);
     case EBM_ENERGY_HARMONIC: return launch_langevin_elem(make_harm(c.e), c);
@@ -435,7 +450,7 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
   EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
   EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
-                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0, nullptr, 0, 0};
+                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0};
   return langevin_dispatch(c);
 }
 
@@ -457,7 +472,7 @@ int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, flo
   const bool fused = e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN;
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, nullptr, 0, 0,
-                 fused ? peer_out_host : nullptr, fused ? world : 0, row_offset};
+                 fused ? peer_out_host : nullptr, fused ? world : 0, row_offset, 0};
   rc = langevin_dispatch(c);
   if (rc || fused) return rc;
   // energies whose burst kernel has no peer-store epilogue yet: copy-engine pushes of the shard into every buffer
@@ -465,6 +480,25 @@ int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, flo
   for (int w = 0; w < world; ++w)
     EBM_CUDA(cudaMemcpyAsync(peer_out_host[w] + row_offset * e->dim, x_out, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
+}
+
+int ebm_langevin_heun_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                                const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                const float* noise, float* traj, int32_t thin, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x_in && x_out && n > 0, "x_in/x_out must be non-null and n positive");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(step_size_host && noise_scale_host, "schedules must be non-null");
+  EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
+  EBM_CHECK_ARG(thin >= 1, "thin must be >= 1");
+  EBM_CHECK_ARG(rng_mode >= EBM_RNG_INJECTED && rng_mode <= EBM_RNG_NATIVE, "bad rng_mode");
+  EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                 rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0, nullptr, 0, 0, 1};
+  return langevin_dispatch(c);
 }
 
 int ebm_pcd_langevin_fused(const EbmEnergyDesc* e) {
@@ -504,7 +538,7 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
   const bool identity = (n == buffer_rows);
   LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream,
-                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr, 0, 0, nullptr, 0, 0};
+                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr, 0, 0, nullptr, 0, 0, 0};
   rc = langevin_dispatch(c);
   if (rc) return rc;
   if (identity) {
@@ -545,7 +579,7 @@ int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, 
         const unsigned long long e1 = (e0 + 4 * wave < numel) ? e0 + 4 * wave : numel;
         EBM_CUDA(cudaMemcpyAsync(scratch_dev + e0, x_in_host + e0, (e1 - e0) * sizeof(float), cudaMemcpyHostToDevice, s));
         LangevinCall c{e, scratch_dev, scratch_dev, n, n_steps, &step_size, &noise_scale, 1, nullptr, rng_mode, seed, offset,
-                       nullptr, nullptr, 1, s, nullptr, nullptr, wave * ck, wave * (ck + 1), nullptr, 0, 0};
+                       nullptr, nullptr, 1, s, nullptr, nullptr, wave * ck, wave * (ck + 1), nullptr, 0, 0, 0};
         rc = langevin_dispatch(c);
         if (rc) return rc;
         EBM_CUDA(cudaMemcpyAsync(x_out_host + e0, scratch_dev + e0, (e1 - e0) * sizeof(float), cudaMemcpyDeviceToHost, s));

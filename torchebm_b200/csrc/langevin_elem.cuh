@@ -53,7 +53,10 @@ struct LangevinElemParams {
   float* peers[kMaxPeers];
 };
 
-template <class EnergyT, int RNG, bool TRAJ, bool CLAMP>
+// HEUN: the two-stage tableau of integrators/heun.py through the reference's generic RK path
+// (core/base_integrator.py:300-347,387-397): k1 = f(x), k2 = f(x + h k1), x1 = x + h (k1/2 + k2/2), then the same noise.
+// The Heun instantiations always compile the clamp in (bounds = -inf / +inf when the sampler has none).
+template <class EnergyT, int RNG, bool TRAJ, bool CLAMP, bool HEUN = false>
 __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constant__ LangevinElemParams P,
                                                             const EnergyT en,
                                                             const __grid_constant__ StepTable tab) {
@@ -124,7 +127,11 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float g = en.grad(x[i]);
+      float g = en.grad(x[i]);
+      if (HEUN) {
+        const float g2 = en.grad(__fsub_rn(x[i], __fmul_rn(h, g)));
+        g = __fadd_rn(__fmul_rn(0.5f, g), __fmul_rn(0.5f, g2));
+      }
       // x1 = x + h*(1.0*(-g)) ; dw = eps*c1 ; x' = x1 + c2*dw   (base_integrator.py:387-397,728-729)
       const float x1 = __fsub_rn(x[i], __fmul_rn(h, g));
       float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(e[i], c1)));

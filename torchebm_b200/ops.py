@@ -92,8 +92,8 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
                    noise_scales: Sequence[float], *, clamp: Optional[Tuple[float, float]] = None,
                    rng_mode: int = _lib.RNG_TORCH, seed: int = 0, offset: int = 0,
                    noise: Optional[torch.Tensor] = None, traj: Optional[torch.Tensor] = None, thin: int = 1,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """K-step burst.  `step_sizes` / `noise_scales` have length 1 (constant) or n_steps.  Returns the final
+                   out: Optional[torch.Tensor] = None, scheme: str = "euler_maruyama") -> torch.Tensor:
+    """K-step burst (`scheme`: "euler_maruyama" or, for the elementwise energies, "heun").  `step_sizes` / `noise_scales` have length 1 (constant) or n_steps.  Returns the final
     state (a new tensor unless `out` is given; `out` may be `x` for an in-place burst)."""
     x = _req(x, "x")
     if out is None:
@@ -104,10 +104,10 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
     hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
     cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
     with torch.cuda.device(x.device):
-        rc = _lib.load().ebm_langevin_burst_f32(
-            C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs, ns, len(step_sizes), cl,
-            int(rng_mode), int(seed), int(offset), _ptr(noise), _ptr(traj), int(thin), _stream(x.device))
-    _lib.check(rc, "ebm_langevin_burst_f32")
+        fn = _lib.load().ebm_langevin_burst_f32 if scheme == "euler_maruyama" else _lib.load().ebm_langevin_heun_burst_f32
+        rc = fn(C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs, ns, len(step_sizes), cl,
+                int(rng_mode), int(seed), int(offset), _ptr(noise), _ptr(traj), int(thin), _stream(x.device))
+    _lib.check(rc, "ebm_langevin_burst_f32" if scheme == "euler_maruyama" else "ebm_langevin_heun_burst_f32")
     return out
 
 

@@ -25,7 +25,7 @@ from torch import nn
 from . import _lib, ops
 from .core import BaseScheduler, EnergyDescriptor, Schedulable, TorchEBMModule, autograd_gradient, energy_descriptor
 from .integrators import (BaseSDERungeKuttaIntegrator, BaseSymplecticIntegrator, EulerMaruyamaIntegrator,
-                          LeapfrogIntegrator, resolve_integrator)
+                          HeunIntegrator, LeapfrogIntegrator, resolve_integrator)
 
 
 class BaseSampler(Schedulable, TorchEBMModule, ABC):
@@ -131,7 +131,10 @@ class LangevinDynamics(BaseSampler):
         n = x.shape[0]
         data_shape = x.shape[1:]
         n_kept = n_steps // thin
-        desc = self._descriptor(x, model_kwargs) if type(self.integrator) is EulerMaruyamaIntegrator else None
+        scheme = {EulerMaruyamaIntegrator: "euler_maruyama", HeunIntegrator: "heun"}.get(type(self.integrator))
+        desc = self._descriptor(x, model_kwargs) if scheme is not None else None
+        if desc is not None and scheme == "heun" and desc.kind not in ("double_well", "harmonic", "rastrigin"):
+            desc = None   # the fused Heun burst exists for the elementwise energies; others step through the integrator
         if desc is None:
             return self._sample_opaque(x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator)
 
@@ -147,7 +150,7 @@ class LangevinDynamics(BaseSampler):
 
         if not return_diagnostics:
             out = ops.langevin_burst(desc, x, n_steps, hs, nss, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
-                                     offset=offset, traj=traj, thin=thin)
+                                     offset=offset, traj=traj, thin=thin, scheme=scheme)
             gen.set_offset(offset + ops.rng_consumed_langevin(self.device, numel, n_steps, rng_mode))
             return traj if return_trajectory else out
 
@@ -159,7 +162,7 @@ class LangevinDynamics(BaseSampler):
             h_j = hs if constant else hs[done:done + thin]
             ns_j = nss if constant else nss[done:done + thin]
             cur = ops.langevin_burst(desc, cur, thin, h_j, ns_j, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
-                                     offset=offset)
+                                     offset=offset, scheme=scheme)
             offset += ops.rng_consumed_langevin(self.device, numel, thin, rng_mode)
             done += thin
             if traj is not None:
@@ -171,7 +174,7 @@ class LangevinDynamics(BaseSampler):
             h_j = hs if constant else hs[done:]
             ns_j = nss if constant else nss[done:]
             cur = ops.langevin_burst(desc, cur, rest, h_j, ns_j, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
-                                     offset=offset)
+                                     offset=offset, scheme=scheme)
             offset += ops.rng_consumed_langevin(self.device, numel, rest, rng_mode)
         gen.set_offset(offset)
         out = traj if return_trajectory else cur
@@ -187,7 +190,7 @@ class LangevinDynamics(BaseSampler):
         Returns `(negatives, new_ptr)`, or None when this sampler / energy has no library kernel for it (the caller
         then takes the three-call path)."""
         if type(self.integrator) is not EulerMaruyamaIntegrator or buffer.ndim != 2 or not buffer.is_cuda:
-            return None
+            return None   # (the one-call PCD path is Euler-Maruyama only)
         self._require_cuda_fp32()
         desc = energy_descriptor(self.model, buffer.shape[1], buffer.device)
         if desc is None or n_steps <= 0:
