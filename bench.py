@@ -62,11 +62,25 @@ def c5_uses_dma(world: int) -> bool:
 
 
 def measured_peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json (burst figures: every kernel here is timed alone),
+    else the fallback of the profiling guide; a malformed or partial file falls back key by key."""
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as f:
-            return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+            data = json.load(f)
+    except (OSError, ValueError):
+        return fallback, "fallback"
+    peaks, kinds = {}, []
+    for key, fb in fallback.items():
+        v = data.get(key) if isinstance(data, dict) else None
+        if isinstance(v, (int, float)) and v > 0:
+            peaks[key] = float(v)
+            kinds.append("measured")
+        else:
+            peaks[key] = fb
+            kinds.append("fallback")
+    return peaks, "measured" if all(k == "measured" for k in kinds) else ("fallback" if all(k == "fallback" for k in kinds) else "mixed " + "/".join(kinds))
 
 
 class ClockSampler:
