@@ -50,6 +50,7 @@ WORKLOADS = {
 }
 WEAK = {"c5"}
 SM_MARGIN = None   # --sm-margin
+C5_GATHER = None   # --c5-gather
 METRIC = "langevin_chain_steps_per_sec"
 UNIT = "chain-steps/s"
 
@@ -58,6 +59,8 @@ def c5_uses_dma(world: int) -> bool:
     """C5 gather policy (measured): peer-to-peer DMA pushes move ~240 GB/s per GPU and take no SM, so
     they hide under the 3.2 ms burst while (world - 1) * 205 MB fits (world <= 4); at 8 GPUs (1.44 GB per GPU per burst)
     NCCL's SM-driven all-gather on 32 SMs left free by the burst is faster (4.67 ms vs 6.14 ms per step)."""
+    if C5_GATHER is not None:
+        return C5_GATHER in ("dma", "sm")
     return world <= 4
 
 
@@ -278,7 +281,8 @@ def make_workload(name: str, n_local: int, dev):
         if name in WEAK and int(os.environ.get("WORLD_SIZE", "1")) > 1:
             # the burst-end gather of burst i runs next to burst i+1: leave it SMs (1 for the barrier kernel of the DMA
             # gather; NCCL's channels need more)
-            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else (1 if c5_uses_dma(int(os.environ.get("WORLD_SIZE", "1"))) else 32)
+            default_margin = 16 if C5_GATHER == "sm" else (1 if c5_uses_dma(int(os.environ.get("WORLD_SIZE", "1"))) else 32)
+            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else default_margin
         cd = te.ContrastiveDivergence(model, sampler, k_steps=k, persistent=True, buffer_size=n_local, init_steps=0,
                                       new_sample_ratio=0.0, device=dev)
         gen = torch.Generator(dev).manual_seed(1234)
@@ -369,7 +373,9 @@ def run_ours(args):
         res.record_stream(side)
         with torch.cuda.stream(side):
             side.wait_event(ready)
-            if peer is not None:
+            if peer is not None and C5_GATHER == "sm":
+                peer.push_sm(res, model.sm_margin)   # peer-store kernel on the SMs the burst leaves free + barrier
+            elif peer is not None:
                 peer.push(res)      # peer-to-peer DMA copies + device barrier: no SM taken from the running burst
             else:
                 gather_chains(res, out=gathered)
@@ -656,11 +662,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: use the NCCL all-gather instead of fused peer stores")
     ap.add_argument("--sm-margin", type=int, default=None, help="c5, N > 1: SMs the persistent burst leaves to the gather")
+    ap.add_argument("--c5-gather", default=None, choices=["dma", "sm", "nccl"],
+                    help="c5, N > 1: peer DMA copies, SM-driven peer-store kernel on the spare SMs, or NCCL (default by world size)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    global SM_MARGIN
+    global SM_MARGIN, C5_GATHER
     SM_MARGIN = args.sm_margin
+    C5_GATHER = args.c5_gather
     if args.impl == "reference":
         run_reference(args)
     else:

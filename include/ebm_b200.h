@@ -155,6 +155,13 @@ int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, flo
                                   const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
                                   float* const* peer_out_host, int32_t world, int64_t row_offset, void* stream);
 
+/* Burst-end gather for bursts whose kernel has no peer-store epilogue: store src[numel] at element offset `elem_offset`
+ * of every rank's gathered buffer (peer_out_host as in ebm_langevin_burst_gather_f32) with at most `max_ctas` CTAs of
+ * 1024 threads, so that it can run on the SMs a persistent burst leaves free (EbmEnergyDesc.sm_margin) on another
+ * stream.  Pointers and offset 16-byte aligned.  A cross-rank barrier must follow. */
+int ebm_peer_push_f32(const float* src, int64_t numel, float* const* peer_out_host, int32_t world, int64_t elem_offset,
+                      int32_t max_ctas, void* stream);
+
 /* Same burst with HOST buffers: copies x_in_host -> device scratch, runs the burst, copies the result
  * back into x_out_host and synchronises `stream`.  `scratch_dev` must hold n*dim floats.
  * Energy parameter buffers in `e` stay device pointers.  Used for the end-to-end measurement. */

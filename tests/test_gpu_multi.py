@@ -73,6 +73,13 @@ def _worker(rank, world, port, n_total, d, k, result_dir):
         want = gather_chains(prev)
         ok = bool(torch.equal(buf.tensor, want))
         results["mlp_push"] = ok
+        # SM-driven push kernel (a few CTAs on the SMs the burst leaves free)
+        buf.tensor.fill_(float("nan"))
+        buf.barrier()
+        odd = x_local[:, :d].contiguous()
+        buf.push_sm(odd, 8)
+        torch.cuda.synchronize()
+        results["mlp_push_sm"] = bool(torch.equal(buf.tensor, gather_chains(odd)))
         torch.save(results, os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()

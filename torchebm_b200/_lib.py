@@ -69,6 +69,7 @@ PROTOTYPES = {
     "ebm_euler_maruyama_step_f32": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _F64, _P]),
     "ebm_langevin_burst_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _PD, _PD, _I32, _PF, _I32, _U64, _U64, _P, _P, _I32, _P]),
     "ebm_langevin_heun_burst_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _PD, _PD, _I32, _PF, _I32, _U64, _U64, _P, _P, _I32, _P]),
+    "ebm_peer_push_f32": (C.c_int, [_P, _I64, C.POINTER(C.c_void_p), _I32, _I64, _I32, _P]),
     "ebm_descent_burst_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _PD, _I32, _F64, _P, _P, _I32, _P]),
     "ebm_langevin_burst_gather_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _PD, _PD, _I32, _PF, _I32, _U64, _U64,
                                                 C.POINTER(C.c_void_p), _I32, _I64, _P]),

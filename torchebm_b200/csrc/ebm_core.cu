@@ -337,6 +337,45 @@ static int launch_descent_elem(const ElemE& en, const EbmEnergyDesc* e, const fl
 int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                              cudaStream_t st);  // ebm_mlp.cu
 
+// SM-driven gather push: every thread streams 16-byte pieces of this rank's shard into all gathered buffers (local
+// and peer-mapped).  Launched with a handful of CTAs next to a persistent burst that leaves as many SMs free
+// (EbmEnergyDesc.sm_margin): NVLink takes stores from SMs at several times the rate of one copy engine.
+struct PeerPushParams {
+  const float4* src;
+  long long n_vec;       // float4 count (tail handled by the last thread below)
+  const float* src_tail;
+  int n_tail;            // 0..3 trailing floats
+  long long dst_off;     // element offset of this rank's shard inside every gathered buffer
+  int world;
+  float* peers[kMaxPeers];
+};
+__global__ void __launch_bounds__(1024) peer_push_kernel(const __grid_constant__ PeerPushParams P) {
+  // 8 independent 16-byte loads in flight per thread (a few CTAs must cover the HBM latency on their own), then the
+  // stores of each piece to every destination
+  constexpr int U = 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < P.n_vec; base += stride * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + u * stride;
+      if (i < P.n_vec) v[u] = __ldcs(P.src + i);
+    }
+    for (int w = 0; w < P.world; ++w) {
+      float4* dst = reinterpret_cast<float4*>(P.peers[w] + P.dst_off);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = base + u * stride;
+        if (i < P.n_vec) dst[i] = v[u];
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < P.n_tail) {
+    const float v = P.src_tail[threadIdx.x];
+    for (int w = 0; w < P.world; ++w) P.peers[w][P.dst_off + 4 * P.n_vec + threadIdx.x] = v;
+  }
+}
+
 // three non-blocking streams per device for the host-buffer entry point (module cache, created on first use);
 // NULL when they cannot be created -- the caller then runs the single-stream path
 static cudaStream_t* host_pipe_streams(int device) {
@@ -499,6 +538,30 @@ int ebm_langevin_heun_burst_f32(const EbmEnergyDesc* e, const float* x_in, float
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, noise, traj, thin, (cudaStream_t)stream, nullptr, nullptr, 0, 0, nullptr, 0, 0, 1};
   return langevin_dispatch(c);
+}
+
+int ebm_peer_push_f32(const float* src, int64_t numel, float* const* peer_out_host, int32_t world, int64_t elem_offset,
+                      int32_t max_ctas, void* stream) {
+  EBM_CHECK_ARG(src && numel > 0 && peer_out_host, "src/peer_out_host must be non-null and numel positive");
+  EBM_CHECK_ARG(world >= 1 && world <= kMaxPeers, "world must be 1..16");
+  EBM_CHECK_ARG(elem_offset >= 0 && max_ctas >= 1, "elem_offset must be non-negative and max_ctas positive");
+  PeerPushParams P;
+  memset(&P, 0, sizeof(P));
+  bool aligned = ((uintptr_t)src & 15) == 0 && (elem_offset % 4) == 0;
+  for (int w = 0; w < world; ++w) {
+    EBM_CHECK_ARG(peer_out_host[w], "null peer pointer");
+    aligned = aligned && ((uintptr_t)peer_out_host[w] & 15) == 0;
+    P.peers[w] = peer_out_host[w];
+  }
+  EBM_CHECK_ARG(aligned, "src, the gathered buffers and elem_offset must be 16-byte aligned");
+  P.src = reinterpret_cast<const float4*>(src);
+  P.n_vec = numel / 4;
+  P.src_tail = src + 4 * P.n_vec;
+  P.n_tail = (int)(numel - 4 * P.n_vec);
+  P.dst_off = elem_offset;
+  P.world = world;
+  peer_push_kernel<<<max_ctas, 1024, 0, (cudaStream_t)stream>>>(P);
+  return launch_status("peer_push_kernel");
 }
 
 int ebm_pcd_langevin_fused(const EbmEnergyDesc* e) {

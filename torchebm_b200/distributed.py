@@ -128,6 +128,16 @@ class PeerGatherBuffer:
             dst[lo:lo + self.rows_per_rank].copy_(x_local, non_blocking=True)
         self.barrier()
 
+    def push_sm(self, x_local: torch.Tensor, max_ctas: int) -> None:
+        """SM-driven gather: a small kernel (`max_ctas` CTAs, to fit the SMs a persistent burst leaves free through
+        `sm_margin`) stores this rank's shard into every rank's gathered tensor over NVLink, then the barrier."""
+        from . import ops
+
+        if x_local.shape[0] != self.rows_per_rank:
+            raise ValueError("every rank must hold n_total / world chains")
+        ops.peer_push(x_local.contiguous(), self.ptrs, self.rank * self.rows_per_rank * self.tensor.shape[1], max_ctas)
+        self.barrier()
+
     def burst(self, desc, x_local: torch.Tensor, n_steps: int, step_sizes, noise_scales, **kw) -> torch.Tensor:
         """Run this rank's burst and push the result into every rank's gathered tensor; returns the local result.
         The gathered tensor is complete on all ranks after the barrier this method issues."""

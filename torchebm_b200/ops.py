@@ -150,6 +150,16 @@ def descent_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_si
     return out
 
 
+def peer_push(x_local: torch.Tensor, peer_ptrs: Sequence[int], elem_offset: int, max_ctas: int) -> None:
+    """SM-driven gather push of a finished shard into every rank's gathered buffer (at most `max_ctas` CTAs)."""
+    x_local = _req(x_local, "x_local")
+    peers = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(x_local.device):
+        rc = _lib.load().ebm_peer_push_f32(x_local.data_ptr(), x_local.numel(), peers, len(peer_ptrs), int(elem_offset),
+                                           int(max_ctas), _stream(x_local.device))
+    _lib.check(rc, "ebm_peer_push_f32")
+
+
 def leapfrog(desc: EnergyDescriptor, x: torch.Tensor, p: torch.Tensor, step_size: float, n_steps: int,
              mass=None, safe: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     x, p = _req(x, "x"), _req(p, "p")
