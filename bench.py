@@ -55,13 +55,15 @@ METRIC = "langevin_chain_steps_per_sec"
 UNIT = "chain-steps/s"
 
 
-def c5_uses_dma(world: int) -> bool:
-    """C5 gather policy (measured): peer-to-peer DMA pushes move ~240 GB/s per GPU and take no SM, so
-    they hide under the 3.2 ms burst while (world - 1) * 205 MB fits (world <= 4); at 8 GPUs (1.44 GB per GPU per burst)
-    NCCL's SM-driven all-gather on 32 SMs left free by the burst is faster (4.67 ms vs 6.14 ms per step)."""
+def c5_gather_mode(world: int) -> str:
+    """C5 gather policy (measured on this pool).  "dma": peer-to-peer copy-engine pushes, no SM used,
+    ~240 GB/s per GPU -- they hide under the 3.2 ms burst while (world - 1) * 205 MB fits (world <= 4: 95 % weak-scaling
+    efficiency at 2 GPUs).  "sm": the burst leaves 16 SMs to a peer-store kernel (ebm_peer_push_f32) -- 4.27 ms per step
+    at 8 GPUs (1.44 GB out and in per GPU per burst), against 4.67 ms for "nccl" (all-gather on 32 spare SMs) and 6.14 ms
+    for DMA pushes."""
     if C5_GATHER is not None:
-        return C5_GATHER in ("dma", "sm")
-    return world <= 4
+        return C5_GATHER
+    return "dma" if world <= 4 else "sm"
 
 
 def measured_peaks():
@@ -281,8 +283,8 @@ def make_workload(name: str, n_local: int, dev):
         if name in WEAK and int(os.environ.get("WORLD_SIZE", "1")) > 1:
             # the burst-end gather of burst i runs next to burst i+1: leave it SMs (1 for the barrier kernel of the DMA
             # gather; NCCL's channels need more)
-            default_margin = 16 if C5_GATHER == "sm" else (1 if c5_uses_dma(int(os.environ.get("WORLD_SIZE", "1"))) else 32)
-            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else default_margin
+            mode = c5_gather_mode(int(os.environ.get("WORLD_SIZE", "1")))
+            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else {"dma": 1, "sm": 16, "nccl": 32}[mode]
         cd = te.ContrastiveDivergence(model, sampler, k_steps=k, persistent=True, buffer_size=n_local, init_steps=0,
                                       new_sample_ratio=0.0, device=dev)
         gen = torch.Generator(dev).manual_seed(1234)
@@ -331,7 +333,7 @@ def run_ours(args):
     # C2 at N > 1: the burst kernel stores its shard straight into every rank's gathered tensor (symmetric memory, NVLink
     # peer stores) and a device-side barrier replaces the NCCL all-gather; NCCL stays the fallback if peer mapping fails
     peer = None
-    want_peer = args.workload == "c2" or (args.workload == "c5" and c5_uses_dma(world))
+    want_peer = args.workload == "c2" or (args.workload == "c5" and c5_gather_mode(world) in ("dma", "sm"))
     if world > 1 and want_peer and not args.nccl_gather:
         ok = torch.ones(1, device=dev)
         try:
@@ -373,7 +375,7 @@ def run_ours(args):
         res.record_stream(side)
         with torch.cuda.stream(side):
             side.wait_event(ready)
-            if peer is not None and C5_GATHER == "sm":
+            if peer is not None and c5_gather_mode(world) == "sm":
                 peer.push_sm(res, model.sm_margin)   # peer-store kernel on the SMs the burst leaves free + barrier
             elif peer is not None:
                 peer.push(res)      # peer-to-peer DMA copies + device barrier: no SM taken from the running burst
@@ -484,6 +486,9 @@ def run_ours(args):
                    "chains_per_gpu": n_local, "collective": ("none" if world == 1 else
                                   "burst-end gather fused into the kernel's final store (NVLink peer stores into symmetric "
                                   "memory) + device-side barrier" if fused_gather else
+                                  "burst-end gather by a peer-store kernel on 16 SMs the burst leaves free (NVLink stores into "
+                                  "symmetric memory) + device-side barrier, on a side stream under the next burst"
+                                  if (peer is not None and c5_gather_mode(world) == "sm") else
                                   "burst-end gather as peer-to-peer DMA copies into symmetric memory + device-side barrier, on a "
                                   "side stream under the next burst" if peer is not None else
                                   "NCCL all_gather of [N/W, D] shards at burst end, on a side stream under the next burst"
