@@ -1,0 +1,51 @@
+"""Host-side pieces of bench.py that need no GPU: workload table, roofline denominators, gather policy."""
+
+import importlib.util
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod
+
+
+def test_workloads_cover_the_baseline_configs():
+    b = _bench()
+    cfgs = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    assert len(cfgs) == 5
+    for name, (n, d, k) in {"c1": (1024, 2, 100), "c2": (65536, 128, 500), "c3": (65536, 784, 20), "c4": (262144, 64, 20),
+                            "c5": (65536, 784, 20)}.items():
+        assert b.WORKLOADS[name][1:] == (n, d, k)
+    assert "c5" in b.WEAK and b.METRIC == "langevin_chain_steps_per_sec"
+
+
+def test_measured_peaks_fallback_and_partial_file(tmp_path, monkeypatch):
+    b = _bench()
+    monkeypatch.setattr(b, "ROOT", str(tmp_path))
+    peaks, kind = b.measured_peaks()
+    assert kind == "fallback" and peaks == {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm_gbs": 6437.3, "bf16_tflops": 1675.2, "bf16_tflops_sustained": 1409.4}))
+    peaks, kind = b.measured_peaks()
+    assert kind == "measured" and peaks["hbm_gbs"] == 6437.3 and peaks["bf16_tflops"] == 1675.2
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm_gbs": 6437.3}))
+    peaks, kind = b.measured_peaks()
+    assert kind.startswith("mixed") and peaks["bf16_tflops"] == 1590.0
+    (tmp_path / "MEASURED_PEAKS.json").write_text("not json")
+    assert b.measured_peaks()[1] == "fallback"
+
+
+def test_c5_gather_policy():
+    b = _bench()
+    assert [b.c5_gather_mode(w) for w in (2, 4, 8)] == ["dma", "dma", "sm"]
+    b.C5_GATHER = "nccl"
+    assert b.c5_gather_mode(2) == "nccl"
