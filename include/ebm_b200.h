@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 5
+#define EBM_ABI_VERSION 6
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -202,18 +202,45 @@ int ebm_pcd_gather_f32(const float* buffer, int64_t buffer_rows, int64_t row_ele
 int ebm_pcd_scatter_f32(float* buffer, int64_t buffer_rows, int64_t row_elems, int64_t ptr,
                         const float* samples, int64_t batch, int64_t* new_ptr_host, void* stream);
 
-/* Persistent-CD negative sampling in one call: start points buffer[idx[i], :] (get_start_points without exploration
- * noise, core/base_loss.py:293-314), n_steps Langevin steps into x_out[n, dim], FIFO write-back of x_out into the
- * buffer at `ptr` (update_buffer, :390-426).  For energies with ebm_pcd_langevin_fused(e) != 0 the gather is the burst
- * kernel's first load and, when n == buffer_rows (idx is then the identity by construction and the whole buffer is
- * replaced), the write-back is its last store: no extra pass over the buffer.  Other energies run gather -> burst ->
- * scatter and need `scratch` [n, dim].  Row length of the buffer = e->dim.  *new_ptr_host receives the new ptr. */
+/* Persistent-CD negative sampling in one call (the sampling half of ContrastiveDivergence.forward,
+ * losses/contrastive_divergence.py:127-139): start points buffer[idx[i], :] (get_start_points, core/base_loss.py:293-314)
+ * plus the exploration noise 0.01 * noise[j, :] on chain noise_rows[j] (:317-332; n_noise may be 0), n_steps Langevin
+ * steps into x_out[n, dim], FIFO write-back of x_out into the buffer at `ptr` (update_buffer, :390-426), and, when
+ * energy_out != NULL, E(x-) of the negatives into energy_out[n].
+ *   idx == NULL states that chain i starts from row i (the reference's stratified draw at stride 1).  With
+ *   n == buffer_rows the write-back then replaces the whole buffer, and for energies with ebm_pcd_langevin_fused(e) != 0
+ *   the burst kernel reads its start rows from the buffer and writes its final state to both destinations: no gather or
+ *   scatter pass; the noise is added in place to the noised rows first.  Any explicit idx runs gather -> burst ->
+ *   scatter and needs `scratch` [n, dim].  Row length of the buffer = e->dim.  *new_ptr_host receives the new ptr. */
 int ebm_pcd_langevin_fused(const EbmEnergyDesc* e);
 int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
                                int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
                                const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                               const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
                                int64_t* new_ptr_host, void* stream);
+
+/* Bursts that also produce the reference's per-kept-sample diagnostics (return_diagnostics=True:
+ * samplers/langevin_dynamics.py:170-185, samplers/hmc.py:294-310) in the same call:
+ *   diag_mean / diag_var [n_kept, dim]: batch mean and biased variance (clamped to [1e-10, 1e10]; 0 for one chain),
+ *   diag_energy [n_kept]: batch mean of E(x) (HMC: of the energies clamped to +-1e10),
+ *   diag_accept [n_kept] (HMC): acceptance fraction of the kept proposal;  n_kept = n_steps / thin >= 1.
+ * diag_ws: n_kept * (2*dim + 2) doubles of device scratch (sums are accumulated in fp64); scratch: n floats;
+ * accept_count (HMC): n_proposals int32 of device scratch.  Elementwise energies accumulate inside the Langevin burst
+ * kernel (one launch + finalize); every other case runs one sub-burst per kept sample followed by the energy and
+ * column-statistics kernels, still inside this one call.  Other arguments as in the plain bursts; heun != 0 selects
+ * the Heun scheme. */
+int ebm_langevin_burst_diag_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                                const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                const float* noise, float* traj, int32_t thin, int32_t heun, double* diag_ws,
+                                float* scratch, float* diag_mean, float* diag_var, float* diag_energy, void* stream);
+int ebm_hmc_burst_diag_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_proposals,
+                           int32_t n_leapfrog, const double* step_size_host, int32_t schedule_len, int32_t mass_kind,
+                           double mass_scalar, const float* mass_vec, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                           const float* noise_p, const float* noise_u, float* traj, int32_t thin, double* diag_ws,
+                           float* scratch, int32_t* accept_count, float* diag_mean, float* diag_var, float* diag_energy,
+                           float* diag_accept, void* stream);
 
 /* Fill out[numel] with the TORCH- or NATIVE-layout normal (kind 0) / uniform (kind 1) stream at
  * (seed, offset): test hook that exposes exactly what the fused kernels draw. */

@@ -223,7 +223,7 @@ def test_mlp_tensor_core_kernel_many_tiles_trajectory_and_native_rng(precision):
                         generator=torch.Generator(DEV).manual_seed(9))
     assert got.shape == (n, 3, 100)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
-    sn = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, device=DEV, rng="native")
+    sn = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, device=DEV).with_rng("native")
     a = sn.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(1))
     b = sn.sample(x=x0, n_steps=5, generator=torch.Generator(DEV).manual_seed(1))
     assert torch.equal(a, b) and torch.isfinite(a).all()
@@ -263,7 +263,7 @@ def test_wide_mlp_kernel_many_tiles_ragged_dims_trajectory(d, hidden, act):
     torch.testing.assert_close(ops.gradient(desc, x0[:333]), en.gradient(x0[:333]), rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(ops.energy(desc, x0[:333]), en.energy(x0[:333]).detach(), rtol=1e-5, atol=1e-4)
     # native stream: deterministic, finite, and a scheduled (per-step table) burst equals the constant one
-    sn = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, device=DEV, rng="native")
+    sn = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, device=DEV).with_rng("native")
     a = sn.sample(x=x0, n_steps=3, generator=torch.Generator(DEV).manual_seed(1))
     b = sn.sample(x=x0, n_steps=3, generator=torch.Generator(DEV).manual_seed(1))
     assert torch.equal(a, b) and torch.isfinite(a).all()
@@ -332,7 +332,7 @@ def test_input_not_mutated_and_in_place_variant():
 def test_native_rng_is_deterministic_and_well_distributed():
     import torchebm_b200 as te
 
-    sampler = te.LangevinDynamics(te.HarmonicModel(k=1.0), step_size=0.05, noise_scale=1.0, device=DEV, rng="native")
+    sampler = te.LangevinDynamics(te.HarmonicModel(k=1.0), step_size=0.05, noise_scale=1.0, device=DEV).with_rng("native")
     x0 = torch.zeros(20000, 8, device=DEV)
     a = sampler.sample(x=x0, n_steps=400, generator=torch.Generator(DEV).manual_seed(1))
     b = sampler.sample(x=x0, n_steps=400, generator=torch.Generator(DEV).manual_seed(1))

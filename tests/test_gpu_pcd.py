@@ -127,7 +127,7 @@ def test_c3_full_size_cd_step_properties():
     model = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(DEV)
 
     def make(ns=1.0, m=model):
-        sampler = te.LangevinDynamics(m, step_size=0.01, noise_scale=ns, device=DEV, rng="native")
+        sampler = te.LangevinDynamics(m, step_size=0.01, noise_scale=ns, device=DEV).with_rng("native")
         return te.ContrastiveDivergence(m, sampler, k_steps=k, persistent=True, buffer_size=n, init_steps=0,
                                         new_sample_ratio=0.0, device=DEV)
 
@@ -147,14 +147,14 @@ def test_c3_full_size_cd_step_properties():
     with torch.no_grad():
         for p in flat.parameters():
             p.zero_()
-    s = te.LangevinDynamics(flat, step_size=0.01, noise_scale=0.7, device=DEV, rng="native")
+    s = te.LangevinDynamics(flat, step_size=0.01, noise_scale=0.7, device=DEV).with_rng("native")
     x0 = torch.randn(n, d, device=DEV)
     dx = s.sample(x=x0, n_steps=k, generator=torch.Generator(DEV).manual_seed(3)) - x0
     var = 2 * 0.01 * k * 0.7 ** 2
     assert abs(dx.mean().item()) < 5e-4 and abs(dx.var().item() / var - 1.0) < 5e-3
     assert abs(dx.var(dim=0).mean().item() / var - 1.0) < 5e-3 and abs((dx[:, :392] * dx[:, 392:]).mean().item()) < 5e-4
 
-    quiet = te.LangevinDynamics(model, step_size=0.01, noise_scale=1e-4, device=DEV, rng="native")
+    quiet = te.LangevinDynamics(model, step_size=0.01, noise_scale=1e-4, device=DEV).with_rng("native")
     with torch.no_grad():
         e0 = model(x0)
         e1 = model(quiet.sample(x=x0, n_steps=k, generator=torch.Generator(DEV).manual_seed(4)))
@@ -164,7 +164,8 @@ def test_c3_full_size_cd_step_properties():
 @pytest.mark.parametrize("d,buffer_size,batch", [(784, 300, 300), (784, 700, 300), (64, 33000, 33000), (64, 40000, 4096),
                                                   (64, 100, 300)])
 @pytest.mark.parametrize("rng", ["torch", "native"])
-def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rng):
+@pytest.mark.parametrize("ratio", [0.0, 0.05, 0.25])
+def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rng, ratio):
     """`sample_negatives` (one library call: start rows read through the index inside the burst kernel, final state
     written straight back into the buffer when buffer_size == batch) must leave exactly the negatives, the buffer, the
     FIFO pointer and the generator that get_start_points -> sample -> update_buffer leave."""
@@ -176,9 +177,9 @@ def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rn
     model = te.MLPEnergy(dim=d, hidden=(128, 96), activation="silu").to(DEV)
 
     def make():
-        sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV, rng=rng)
+        sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV).with_rng(rng)
         return te.ContrastiveDivergence(model, sampler, k_steps=4, persistent=True, buffer_size=buffer_size, init_steps=0,
-                                        new_sample_ratio=0.0, device=DEV)
+                                        new_sample_ratio=ratio, device=DEV)
 
     a, b = make(), make()
     ga, gb = torch.Generator(DEV).manual_seed(21), torch.Generator(DEV).manual_seed(21)
@@ -194,6 +195,13 @@ def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rn
             assert torch.equal(a.replay_buffer, b.replay_buffer)
             assert a._buffer_ptr_int == b._buffer_ptr_int and int(a.buffer_ptr) == int(b.buffer_ptr)
             assert ga.get_offset() == gb.get_offset()
+    # E(x-) of the negatives from the same call (contrastive_divergence.py:184-223 needs it for the loss value)
+    e_out = torch.empty(batch, device=DEV)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        neg = a.sample_negatives(data[0], generator=ga, energy_out=e_out)
+    with torch.no_grad():
+        torch.testing.assert_close(e_out, model(neg), rtol=1e-4, atol=1e-4)
 
 
 def test_fused_pcd_falls_back_for_analytic_energies_and_matches_reference_golden():

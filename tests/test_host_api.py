@@ -9,7 +9,7 @@ import torch
 
 import torchebm_b200 as te
 from torchebm_b200 import _lib
-from torchebm_b200.core import ConstantScheduler, energy_descriptor, mark_mlp_energy
+from torchebm_b200.core import advance_schedules, energy_descriptor, mark_mlp_energy
 
 
 def test_sample_signature_matches_reference_contract():
@@ -27,8 +27,13 @@ def test_sample_signature_matches_reference_contract():
         assert not any(p.kind in (p.VAR_POSITIONAL, p.VAR_KEYWORD) for p in sig.parameters.values())
         ctor = list(inspect.signature(cls.__init__).parameters)
         assert ctor[1] == "model" and ctor.index("dtype") < ctor.index("device")
-        if "integrator" in ctor:
-            assert ctor.index("device") < ctor.index("integrator")
+        if "integrator" in ctor:   # test_api_contract.py:199-201: `integrator` is the LAST constructor parameter
+            assert ctor[-1] == "integrator" and ctor.index("device") < ctor.index("integrator")
+        assert "rng" not in ctor   # the RNG layout is an attribute, not a constructor argument
+    s = te.LangevinDynamics(te.DoubleWellModel())
+    assert s.rng == "torch" and s.with_rng("native").rng == "native"
+    with pytest.raises(ValueError, match="rng must be"):
+        s.rng = "mt19937"
 
 
 def test_constructor_validation():
@@ -49,15 +54,24 @@ def test_constructor_validation():
         te.LangevinDynamics(m, dtype=torch.float32, integrator=te.EulerMaruyamaIntegrator(dtype=torch.float64))
 
 
-def test_cpu_sampler_raises_loudly():
+def test_cpu_sampler_has_no_path_of_its_own():
+    """A CPU sampler never runs code of this package: the standalone classes raise, the reference-derived ones hand the
+    call to the reference's own `sample()` (and say so in `last_path`)."""
     s = te.LangevinDynamics(te.DoubleWellModel(), step_size=0.01)
-    with pytest.raises(RuntimeError, match="CUDA device only"):
-        s.sample(dim=2, n_steps=2)
-    for other in (te.GradientDescentSampler(te.DoubleWellModel(), step_size=0.01),
-                  te.NesterovSampler(te.DoubleWellModel(), step_size=0.01, momentum=0.5),
-                  te.HamiltonianMonteCarlo(te.DoubleWellModel(), step_size=0.01)):
-        with pytest.raises(RuntimeError, match="CUDA device only"):
-            other.sample(dim=2, n_steps=2)
+    others = (te.GradientDescentSampler(te.DoubleWellModel(), step_size=0.01),
+              te.NesterovSampler(te.DoubleWellModel(), step_size=0.01, momentum=0.5),
+              te.HamiltonianMonteCarlo(te.DoubleWellModel(), step_size=0.01))
+    if te.REFERENCE_DERIVED:
+        import torchebm
+
+        for smp in (s,) + others:
+            assert isinstance(smp, torchebm.core.BaseSampler)
+            out = smp.sample(dim=2, n_samples=3, n_steps=2)
+            assert out.shape == (3, 2) and out.device.type == "cpu" and smp.last_path == "unfused"
+    else:
+        for smp in (s,) + others:
+            with pytest.raises(RuntimeError, match="CUDA device only"):
+                smp.sample(dim=2, n_steps=2)
     with pytest.raises(ValueError, match="momentum must be in"):
         te.NesterovSampler(te.DoubleWellModel(), momentum=1.5)
     # the persistent-CD one-call path declines (None) instead of touching a CPU buffer
@@ -82,15 +96,15 @@ def test_scheduler_values_follow_reference_formulas():
 def test_advance_schedules_semantics():
     # langevin_dynamics.py:161-168: step i uses the value after i .step() calls; step_count == n_steps afterwards
     s = te.LangevinDynamics(te.DoubleWellModel(), step_size=te.LinearScheduler(0.1, 0.01, 5), noise_scale=2.0)
-    vals, constant = s._advance_schedules(("step_size", "noise_scale"), 7)
+    vals, constant = advance_schedules(s, ("step_size", "noise_scale"), 7)
     assert not constant
     assert vals["step_size"][:6] == pytest.approx([0.1, 0.082, 0.064, 0.046, 0.028, 0.01])
     assert vals["noise_scale"] == [2.0] * 7
     assert s.schedulers["step_size"].step_count == 7 and s.schedulers["noise_scale"].step_count == 7
     s2 = te.LangevinDynamics(te.DoubleWellModel(), step_size=0.01)
-    vals, constant = s2._advance_schedules(("step_size", "noise_scale"), 500)
+    vals, constant = advance_schedules(s2, ("step_size", "noise_scale"), 500)
     assert constant and vals == {"step_size": [0.01], "noise_scale": [1.0]}
-    assert all(isinstance(v, ConstantScheduler) and v.step_count == 500 for v in s2.schedulers.values())
+    assert all(isinstance(v, te.ConstantScheduler) and v.step_count == 500 for v in s2.schedulers.values())
     s2.reset_schedulers()
     assert all(v.step_count == 0 for v in s2.schedulers.values())
 

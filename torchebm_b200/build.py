@@ -59,16 +59,24 @@ def is_current() -> bool:
         return f.read().strip() == _digest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and is_current():
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B build of the same ABI with extra -D flags -> lib/libebm_b200_<name>.so; load it with EBM_B200_LIB=<path>
+    (kernel tuning only: the default library is what ships and what the tests run)."""
+    return build(force=True, verbose=verbose, extra=[f"-D{d}" for d in defines], tag=name)
+
+
+def build(force: bool = False, verbose: bool = False, extra=(), tag: str = "") -> str:
+    if not tag and not force and is_current():
         return LIB
     nvcc = _nvcc()
-    os.makedirs(OBJ, exist_ok=True)
+    obj_dir = os.path.join(OBJ, tag) if tag else OBJ
+    lib_path = os.path.join(LIBDIR, f"libebm_b200_{tag}.so") if tag else LIB
+    os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -80,16 +88,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    with open(os.path.join(LIBDIR, "build.stamp"), "w") as f:
-        f.write(_digest())
-    return LIB
+    if not tag:
+        with open(os.path.join(LIBDIR, "build.stamp"), "w") as f:
+            f.write(_digest())
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(path)
+    if "--variant" in sys.argv:   # python -m torchebm_b200.build --variant NAME DEFINE[=VALUE] ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if not a.startswith("--")], verbose="--verbose" in sys.argv))
+    else:
+        path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+        print(path)

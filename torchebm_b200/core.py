@@ -190,12 +190,7 @@ class Schedulable:
         return self.schedulers[name].get_value()
 
     def _subtree_schedulers(self) -> List[BaseScheduler]:
-        out: List[BaseScheduler] = []
-        for m in self.modules():
-            scheds = getattr(m, "schedulers", None)
-            if isinstance(scheds, dict) and hasattr(m, "step_schedulers"):
-                out.extend(scheds.values())
-        return out
+        return subtree_schedulers(self)
 
     def step_schedulers(self) -> None:
         for s in self._subtree_schedulers():
@@ -206,25 +201,40 @@ class Schedulable:
             s.reset()
 
     def _advance_schedules(self, names: Sequence[str], k: int) -> Tuple[Dict[str, List[float]], bool]:
-        """Values each of `names` takes over the next k sampler steps, advancing every scheduler in the
-        subtree k times (langevin_dynamics.py:161-168: read, step, read, step, ...).
+        return advance_schedules(self, names, k)
 
-        Returns (values, constant); when every scheduler in the subtree is a ConstantScheduler the lists
-        have length 1 and only the step counters are bumped."""
-        all_s = self._subtree_schedulers()
-        if all(_is_constant_scheduler(s) for s in all_s):
-            vals = {n: [float(self.get_scheduled_value(n))] for n in names}
-            for s in all_s:
-                s.step_count += k
-                s.current_value = s.start_value
-            return vals, True
-        vals = {n: [] for n in names}
-        for _ in range(k):
-            for n in names:
-                vals[n].append(float(self.get_scheduled_value(n)))
-            for s in all_s:
-                s.step()
-        return vals, False
+
+def subtree_schedulers(module: nn.Module) -> List[Any]:
+    """Every scheduler `module.step_schedulers()` would step (schedulable.py:60-75: the module subtree, each
+    Schedulable's own dict); works on this package's and on the reference's Schedulable alike."""
+    out: List[Any] = []
+    for m in module.modules():
+        scheds = getattr(m, "schedulers", None)
+        if isinstance(scheds, dict) and hasattr(m, "step_schedulers"):
+            out.extend(scheds.values())
+    return out
+
+
+def advance_schedules(module: nn.Module, names: Sequence[str], k: int) -> Tuple[Dict[str, List[float]], bool]:
+    """Values each of `names` takes over the next k sampler steps, advancing every scheduler in the
+    subtree k times (langevin_dynamics.py:161-168: read, step, read, step, ...).
+
+    Returns (values, constant); when every scheduler in the subtree is a ConstantScheduler the lists
+    have length 1 and only the step counters are bumped."""
+    all_s = subtree_schedulers(module)
+    if all(_is_constant_scheduler(s) for s in all_s):
+        vals = {n: [float(module.get_scheduled_value(n))] for n in names}
+        for s in all_s:
+            s.step_count += k
+            s.current_value = s.start_value
+        return vals, True
+    vals = {n: [] for n in names}
+    for _ in range(k):
+        for n in names:
+            vals[n].append(float(module.get_scheduled_value(n)))
+        for s in all_s:
+            s.step()
+    return vals, False
 
 
 # --------------------------------------------------------------------------------------------------
@@ -532,9 +542,10 @@ def mark_mlp_energy(model: nn.Module, probe: Optional[torch.Tensor] = None) -> b
     if own_params != sum(p.numel() for p in seqs[0].parameters()):
         return False
     net = seqs[0]
-    if probe is None:
+    if probe is None:   # deterministic probe: drawing one would advance the global generator of a seeded script
         l1 = net[0]
-        probe = torch.randn(8, l1.in_features, device=l1.weight.device, dtype=l1.weight.dtype)
+        probe = torch.linspace(-2.0, 2.0, 8 * l1.in_features, device=l1.weight.device,
+                               dtype=l1.weight.dtype).reshape(8, l1.in_features)
     with torch.no_grad():
         a = model(probe)
         b = net(probe).squeeze(-1)

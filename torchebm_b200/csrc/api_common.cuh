@@ -165,7 +165,17 @@ struct LangevinCall {
   int n_peers;
   long long peer_row_offset;
   int scheme;   // 0 = Euler-Maruyama, 1 = Heun (elementwise energies only)
+  // in-burst diagnostics (elementwise kernels only): fp64 workspace [n_steps / thin, diag_slot(dim)], see diag.cuh
+  double* diag_ws;
 };
+
+// diagnostics helpers shared by the Langevin and HMC entry points (ebm_core.cu)
+// ws slot += column sums / sums of squares of x[n, d] and the sum of energy[n] (energy may be null)
+int diag_accumulate(double* ws_slot, const float* x, const float* energy, int64_t n, int d, cudaStream_t st);
+// ws -> mean / var [n_kept, d], energy [n_kept] = e_scale * (energy sum / n) + e_shift; accept (may be null):
+// acceptance_rate[j] = accept_count[(j + 1) * thin - 1] / n
+int diag_finalize(const double* ws, int n_kept, int d, int64_t n, float e_scale, float e_shift, float* mean, float* var,
+                  float* energy, const int32_t* accept_count, int thin, float* accept_rate, cudaStream_t st);
 
 inline int row_grid(const DeviceInfo& di, long long n, int G, int ctas_per_sm) {
   const long long rows_per_cta = kRowThreads / G;

@@ -134,17 +134,19 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
   P.has_clamp = c.clamp != nullptr;
   if (c.clamp) { P.clamp_lo = c.clamp[0]; P.clamp_hi = c.clamp[1]; }
   P.traj = c.traj;
+  P.diag_ws = c.diag_ws;
+  const bool keep = c.traj || c.diag_ws;   // the keeping instantiations: trajectory and / or in-burst diagnostics
   if (c.scheme == 1 && !c.clamp) { P.clamp_lo = -INFINITY; P.clamp_hi = INFINITY; }   // the Heun kernel always clamps
   if (c.rng_mode == EBM_RNG_TORCH) {
     P.T = torch_threads(di, numel);
     const unsigned long long J = (((unsigned long long)numel + P.T - 1) / P.T + 3) / 4;
     P.n_quads = P.T * J;
-    P.k0 = (uint32_t)c.seed; P.k1 = (uint32_t)(c.seed >> 32);
+    philox_expand_keys(P.keys, (uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     P.ctr_step = torch_offset_increment(di, numel) / 4;
   } else {
     P.T = 1;
     P.n_quads = ((unsigned long long)numel + 3) / 4;
-    P.k0 = (uint32_t)c.seed ^ kNativeTag0; P.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
+    philox_expand_keys(P.keys, (uint32_t)c.seed ^ kNativeTag0, (uint32_t)(c.seed >> 32) ^ kNativeTag1);
     P.ctr_step = 1;
   }
   P.quad_base = 0;
@@ -180,7 +182,7 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     P.thin_start = c.thin - (done % c.thin);
     P.kept_base = done / c.thin;
 #define LAUNCH(RNG)                                                                                          \
-  if (c.traj) {                                                                                              \
+  if (keep) {                                                                                                \
     if (c.clamp) langevin_elem_kernel<ElemE, RNG, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);   \
     else         langevin_elem_kernel<ElemE, RNG, true, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);  \
   } else {                                                                                                   \
@@ -188,7 +190,7 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     else         langevin_elem_kernel<ElemE, RNG, false, false><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab); \
   }
 #define LAUNCH_HEUN(RNG)                                                                                     \
-  if (c.traj) langevin_elem_kernel<ElemE, RNG, true, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);     \
+  if (keep)   langevin_elem_kernel<ElemE, RNG, true, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);     \
   else        langevin_elem_kernel<ElemE, RNG, false, true, true><<<(unsigned)blocks, 256, 0, c.st>>>(P, en, tab);
     if (c.scheme == 1) {
       if (c.rng_mode == EBM_RNG_INJECTED) { LAUNCH_HEUN(0) }
@@ -393,6 +395,83 @@ static cudaStream_t* host_pipe_streams(int device) {
 }
 size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e);  // ebm_mlp_wide.cu
 
+// ---- diagnostics: column statistics of a state tensor, finalisation (diag.cuh) ------------------------------------
+// CTA = 256 threads = 256 / cw row lanes x cw columns (cw = min(d, 256) rounded to a power of two would waste lanes;
+// simply thread t <-> column (t % cw), row lane (t / cw)); a CTA walks its slab of rows, keeps fp64 partial sums in
+// registers and issues one atomic per (column, row lane) at the end.
+__global__ void __launch_bounds__(256) diag_accumulate_kernel(double* __restrict__ slot, const float* __restrict__ x,
+                                                              const float* __restrict__ energy, long long n, int d,
+                                                              long long rows_per_cta) {
+  const int cw = d < 256 ? d : 256;
+  const int lanes = 256 / cw;               // row lanes of this CTA
+  const int col0 = threadIdx.x % cw, rl = threadIdx.x / cw;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
+  if (rl < lanes) {
+    for (int c = col0; c < d; c += cw) {
+      double s = 0.0, q = 0.0;
+      for (long long r = r0 + rl; r < r1; r += lanes) {
+        const double v = (double)x[r * d + c];
+        s += v;
+        q += v * v;
+      }
+      atomicAdd(slot + c, s);
+      atomicAdd(slot + d + c, q);
+    }
+  }
+  if (energy) {
+    double es = 0.0;
+    for (long long r = r0 + threadIdx.x; r < r1; r += 256) es += (double)energy[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(slot + 2 * d, es);
+  }
+}
+
+__global__ void diag_finalize_kernel(const double* __restrict__ ws, int n_kept, int d, double inv_n, long long n,
+                                     float e_scale, float e_shift, float* __restrict__ mean, float* __restrict__ var,
+                                     float* __restrict__ energy, const int32_t* __restrict__ accept_count, int thin,
+                                     float* __restrict__ accept_rate) {
+  const long long total = (long long)n_kept * d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long j = i / d;
+    const int c = (int)(i - j * d);
+    const double* slot = ws + j * diag_slot(d);
+    const double m = slot[c] * inv_n;
+    mean[i] = (float)m;
+    float v = 0.0f;                                        // one chain: the reference zeroes the variance
+    if (n > 1) {
+      v = (float)(slot[d + c] * inv_n - m * m);            // x.var(dim=0, unbiased=False)
+      v = (v != v) ? v : fminf(fmaxf(v, 1e-10f), 1e10f);   // .clamp_(min=1e-10, max=1e10)
+    }
+    var[i] = v;
+    if (c == 0) {
+      energy[j] = __fadd_rn(__fmul_rn(e_scale, (float)(slot[2 * d] * inv_n)), e_shift);
+      if (accept_rate) accept_rate[j] = (float)accept_count[(j + 1) * thin - 1] / (float)n;
+    }
+  }
+}
+
+int diag_accumulate(double* ws_slot, const float* x, const float* energy, int64_t n, int d, cudaStream_t st) {
+  const DeviceInfo& di = device_info(current_device());
+  long long ctas = (long long)di.sm_count * 4;
+  const long long min_rows = 64;
+  if (ctas * min_rows > n) ctas = (n + min_rows - 1) / min_rows;
+  const long long rows_per_cta = (n + ctas - 1) / ctas;
+  ctas = (n + rows_per_cta - 1) / rows_per_cta;
+  diag_accumulate_kernel<<<(unsigned)ctas, 256, 0, st>>>(ws_slot, x, energy, n, d, rows_per_cta);
+  return launch_status("diag_accumulate_kernel");
+}
+
+int diag_finalize(const double* ws, int n_kept, int d, int64_t n, float e_scale, float e_shift, float* mean, float* var,
+                  float* energy, const int32_t* accept_count, int thin, float* accept_rate, cudaStream_t st) {
+  const DeviceInfo& di = device_info(current_device());
+  diag_finalize_kernel<<<flat_grid(di, (long long)n_kept * d, 256), 256, 0, st>>>(
+      ws, n_kept, d, 1.0 / (double)n, n, e_scale, e_shift, mean, var, energy, accept_count, thin, accept_rate);
+  return launch_status("diag_finalize_kernel");
+}
+
 }  // namespace ebm
 
 using namespace ebm;
@@ -573,42 +652,73 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
                                int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
                                const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                               const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
                                int64_t* new_ptr_host, void* stream) {
   int rc = validate_desc(e);
   if (rc) return rc;
-  EBM_CHECK_ARG(buffer && idx && x_out && buffer_rows > 0 && n > 0, "buffer/idx/x_out must be non-null, sizes positive");
+  EBM_CHECK_ARG(buffer && x_out && buffer_rows > 0 && n > 0, "buffer/x_out must be non-null, sizes positive");
+  EBM_CHECK_ARG(idx || n <= buffer_rows, "idx == NULL (chain i starts from row i) needs n <= buffer_rows");
   EBM_CHECK_ARG(ptr >= 0 && ptr < buffer_rows, "ptr out of range");
   EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
   EBM_CHECK_ARG(step_size_host && noise_scale_host, "schedules must be non-null");
   EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
   EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "the fused PCD burst draws its own noise");
   EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
-  const bool fused = ebm_pcd_langevin_fused(e) != 0;
-  EBM_CHECK_ARG(fused || scratch, "scratch [n, dim] is required for energies without a fused gather");
+  EBM_CHECK_ARG(n_noise == 0 || (noise_rows && noise), "noise_rows/noise must be given when n_noise > 0");
   const int64_t row_elems = e->dim;
-  if (!fused) {  // gather -> burst -> FIFO scatter as three launches
-    rc = ebm_pcd_gather_f32(buffer, buffer_rows, row_elems, idx, n, scratch, nullptr, nullptr, 0, stream);
+  // The one-call form needs (a) a burst kernel that can write its final state to two destinations and (b) chain i
+  // reading and writing row i of the buffer, which the caller states by passing idx == NULL (the reference's
+  // stratified draw with stride 1, core/base_loss.py:307-312, when the batch is the whole buffer the write-back
+  // replaces every row with ptr = 0, :409-413).  Exploration noise (:317-332) is then added in place to the few
+  // noised rows first: every row is overwritten by the write-back anyway.  An explicit idx -- any permutation or
+  // draw with replacement -- always goes gather -> burst -> FIFO scatter.
+  const bool one_call = ebm_pcd_langevin_fused(e) != 0 && idx == nullptr && n == buffer_rows;
+  if (one_call) {
+    if (n_noise > 0) {
+      const DeviceInfo& di = device_info(current_device());
+      pcd_noise_kernel<<<flat_grid(di, n_noise * row_elems, 256), 256, 0, (cudaStream_t)stream>>>(
+          buffer, row_elems, (const long long*)noise_rows, noise, n_noise);
+      rc = launch_status("pcd_noise_kernel");
+      if (rc) return rc;
+    }
+    LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                   rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, buffer, 0, 0, nullptr, 0, 0, 0,
+                   nullptr};
+    rc = langevin_dispatch(c);
+    if (rc) return rc;
+    if (new_ptr_host) *new_ptr_host = 0;
+  } else if (ebm_pcd_langevin_fused(e) != 0 && idx != nullptr && n_noise == 0) {
+    // the burst kernel reads its start rows through idx; the FIFO write-back stays a separate launch (a destination
+    // row may be another chain's source row)
+    LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                   rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, (const long long*)idx, nullptr, 0, 0,
+                   nullptr, 0, 0, 0, nullptr};
+    rc = langevin_dispatch(c);
+    if (rc) return rc;
+    rc = ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
+    if (rc) return rc;
+  } else {   // gather (+ noise) -> burst -> FIFO scatter as separate launches
+    EBM_CHECK_ARG(scratch, "scratch [n, dim] is required unless the burst kernel reads the buffer itself");
+    if (idx) {
+      rc = ebm_pcd_gather_f32(buffer, buffer_rows, row_elems, idx, n, scratch, noise_rows, noise, n_noise, stream);
+    } else {
+      EBM_CUDA(cudaMemcpyAsync(scratch, buffer, (size_t)n * row_elems * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      if (n_noise > 0) {
+        const DeviceInfo& di = device_info(current_device());
+        pcd_noise_kernel<<<flat_grid(di, n_noise * row_elems, 256), 256, 0, (cudaStream_t)stream>>>(
+            scratch, row_elems, (const long long*)noise_rows, noise, n_noise);
+        rc = launch_status("pcd_noise_kernel");
+      }
+    }
     if (rc) return rc;
     rc = ebm_langevin_burst_f32(e, scratch, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len,
                                 clamp_lo_hi_host, rng_mode, seed, offset, nullptr, nullptr, 1, stream);
     if (rc) return rc;
-    return ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
+    rc = ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
+    if (rc) return rc;
   }
-  // n == buffer_rows: the reference's stratified draw has stride 1, i.e. idx is the identity, and the write-back
-  // replaces the whole buffer with ptr = 0 (core/base_loss.py:307-312, :409-413): chain i reads and writes row i,
-  // so the final state can go to both destinations from inside the burst.  Otherwise rows are read through idx and
-  // the FIFO write-back stays a separate launch (a destination row may be another chain's source row).
-  const bool identity = (n == buffer_rows);
-  LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
-                 rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream,
-                 identity ? nullptr : (const long long*)idx, identity ? buffer : nullptr, 0, 0, nullptr, 0, 0, 0};
-  rc = langevin_dispatch(c);
-  if (rc) return rc;
-  if (identity) {
-    if (new_ptr_host) *new_ptr_host = 0;
-    return 0;
-  }
-  return ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
+  if (energy_out) return ebm_energy_f32(e, x_out, n, energy_out, stream);   // E(x-) of the negatives
+  return 0;
 }
 
 int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, float* x_out_host, float* scratch_dev,
@@ -717,6 +827,71 @@ int ebm_pcd_scatter_f32(float* buffer, int64_t buffer_rows, int64_t row_elems, i
   }
   if (new_ptr_host) *new_ptr_host = new_ptr;
   return launch_status("pcd_scatter_kernel");
+}
+
+int ebm_langevin_burst_diag_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
+                                const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                const float* noise, float* traj, int32_t thin, int32_t heun, double* diag_ws,
+                                float* scratch, float* diag_mean, float* diag_var, float* diag_energy, void* stream) {
+  int rc = validate_desc(e);
+  if (rc) return rc;
+  EBM_CHECK_ARG(x_in && x_out && n > 0, "x_in/x_out must be non-null and n positive");
+  EBM_CHECK_ARG(n_steps > 0, "n_steps must be positive");
+  EBM_CHECK_ARG(step_size_host && noise_scale_host, "schedules must be non-null");
+  EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
+  EBM_CHECK_ARG(thin >= 1 && n_steps / thin >= 1, "thin must be >= 1 and keep at least one sample");
+  EBM_CHECK_ARG(rng_mode >= EBM_RNG_INJECTED && rng_mode <= EBM_RNG_NATIVE, "bad rng_mode");
+  EBM_CHECK_ARG(rng_mode != EBM_RNG_INJECTED || noise, "INJECTED rng needs a noise array");
+  EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  EBM_CHECK_ARG(diag_ws && diag_mean && diag_var && diag_energy, "diagnostic outputs and workspace must be non-null");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = e->dim;
+  const int n_kept = n_steps / thin;
+  EBM_CUDA(cudaMemsetAsync(diag_ws, 0, (size_t)n_kept * diag_slot(d) * sizeof(double), st));
+  const bool elem = e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN;
+  if (elem) {   // one burst launch: the kernel accumulates the statistics of every kept sample itself
+    LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
+                   rng_mode, seed, offset, noise, traj, thin, st, nullptr, nullptr, 0, 0, nullptr, 0, 0, heun ? 1 : 0, diag_ws};
+    rc = langevin_dispatch(c);
+    if (rc) return rc;
+    float es = 1.0f, eb = 0.0f;   // energy = finish(sum of terms): h * s, half_k * s, a*D + s
+    if (e->kind == EBM_ENERGY_DOUBLE_WELL) es = e->p[0];
+    else if (e->kind == EBM_ENERGY_HARMONIC) es = e->p[0];
+    else eb = e->p[2];
+    return diag_finalize(diag_ws, n_kept, d, n, es, eb, diag_mean, diag_var, diag_energy, nullptr, thin, nullptr, st);
+  }
+  // other energies: one sub-burst per kept sample, each followed by the energy and column-statistics kernels
+  EBM_CHECK_ARG(scratch, "scratch [n] is required for this energy");
+  EBM_CHECK_ARG(!heun, "the Heun burst is fused for the elementwise energies only");
+  const DeviceInfo& di = device_info(current_device());
+  const long long numel = (long long)n * d;
+  const uint64_t per_step = rng_mode == EBM_RNG_TORCH ? torch_offset_increment(di, numel) : (rng_mode == EBM_RNG_NATIVE ? 4 : 0);
+  const float* src = x_in;
+  int done = 0;
+  for (int j = 0; j <= n_kept; ++j) {
+    const int len = j < n_kept ? thin : n_steps - done;   // the tail after the last kept sample
+    if (len <= 0) break;
+    LangevinCall c{e, src, x_out, n, len, schedule_len == 1 ? step_size_host : step_size_host + done,
+                   schedule_len == 1 ? noise_scale_host : noise_scale_host + done, schedule_len == 1 ? 1 : len,
+                   clamp_lo_hi_host, rng_mode, seed, offset + (uint64_t)done * per_step,
+                   noise ? noise + (long long)done * numel : nullptr, nullptr, 1, st, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0,
+                   nullptr};
+    rc = langevin_dispatch(c);
+    if (rc) return rc;
+    done += len;
+    src = x_out;
+    if (j < n_kept) {
+      rc = ebm_energy_f32(e, x_out, n, scratch, stream);
+      if (rc) return rc;
+      rc = diag_accumulate(diag_ws + (long long)j * diag_slot(d), x_out, scratch, n, d, st);
+      if (rc) return rc;
+      if (traj)   // traj[:, j, :] = x
+        EBM_CUDA(cudaMemcpy2DAsync(traj + (long long)j * d, (size_t)n_kept * d * sizeof(float), x_out, (size_t)d * sizeof(float),
+                                   (size_t)d * sizeof(float), (size_t)n, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return diag_finalize(diag_ws, n_kept, d, n, 1.0f, 0.0f, diag_mean, diag_var, diag_energy, nullptr, thin, nullptr, st);
 }
 
 }  // extern "C"

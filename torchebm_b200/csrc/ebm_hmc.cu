@@ -41,6 +41,13 @@ static int launch_leapfrog(const RowE& en, const EbmEnergyDesc* e, LeapfrogParam
   return launch_status("leapfrog_kernel");
 }
 
+// diagnostics of the kept proposals (ebm_hmc_burst_diag_f32): launches end on kept proposals, whose state statistics
+// and energies are accumulated right after the launch
+struct HmcDiag {
+  double* ws;        // [n_kept, diag_slot(d)], zeroed
+  float* scratch;    // [n] energies of the state after a kept proposal
+};
+
 struct HmcCall {
   const EbmEnergyDesc* e;
   const double* hs;
@@ -49,6 +56,7 @@ struct HmcCall {
   uint64_t offset;
   uint64_t inc_p, inc_u;  // generator offset consumed per proposal by the momentum / uniform draws
   cudaStream_t st;
+  const HmcDiag* diag;
 };
 
 // the proposal loop is launched in chunks of at most kSchedChunk proposals (per-proposal step-size table); `launch`
@@ -63,7 +71,12 @@ static int hmc_chunks(const HmcCall& c, HmcParams& P, Launch launch) {
   float* energy_out = P.energy_out;
   int done = 0;
   while (done < c.n_proposals) {
-    const int chunk = uniform ? c.n_proposals : ((c.n_proposals - done < kSchedChunk) ? (c.n_proposals - done) : kSchedChunk);
+    int chunk = uniform ? c.n_proposals : ((c.n_proposals - done < kSchedChunk) ? (c.n_proposals - done) : kSchedChunk);
+    if (c.diag) {   // end the launch on the next kept proposal (or on the end of the call behind the last kept one)
+      const int to_keep = P.thin - (done % P.thin);
+      if (done / P.thin < P.n_kept && to_keep < chunk) chunk = to_keep;
+      if (chunk > kSchedChunk) chunk = kSchedChunk;
+    }
     HStepTable tab;
     memset(&tab, 0, sizeof(tab));
     if (uniform) { tab.h[0] = (float)c.hs[0]; tab.mask = 0; }
@@ -76,6 +89,8 @@ static int hmc_chunks(const HmcCall& c, HmcParams& P, Launch launch) {
     P.thin_start = P.thin - (done % P.thin);
     P.kept_base = done / P.thin;
     P.energy_out = (done + chunk >= c.n_proposals) ? energy_out : nullptr;
+    const bool kept_here = c.diag && ((done + chunk) % P.thin == 0) && ((done + chunk) / P.thin <= P.n_kept);
+    if (kept_here) P.energy_out = c.diag->scratch;
     if (P.rng_p.mode == EBM_RNG_TORCH) {
       P.rng_p.ctr_base = (c.offset + (uint64_t)done * (c.inc_p + c.inc_u)) / 4;
       P.rng_u.ctr_base = (c.offset + (uint64_t)done * (c.inc_p + c.inc_u) + c.inc_p) / 4;
@@ -87,6 +102,13 @@ static int hmc_chunks(const HmcCall& c, HmcParams& P, Launch launch) {
     if (rc) return rc;
     done += chunk;
     x_src = P.x_out;
+    if (kept_here) {
+      rc = diag_accumulate(c.diag->ws + (long long)(done / P.thin - 1) * diag_slot(P.d), P.x_out, c.diag->scratch, P.n, P.d, c.st);
+      if (rc) return rc;
+      if (energy_out && done >= c.n_proposals)
+        if (cudaMemcpyAsync(energy_out, c.diag->scratch, (size_t)P.n * sizeof(float), cudaMemcpyDeviceToDevice, c.st) != cudaSuccess)
+          return (int)cudaGetLastError();
+    }
   }
   return 0;
 }
@@ -145,11 +167,11 @@ int ebm_leapfrog_f32(const EbmEnergyDesc* e, const float* x_in, const float* p_i
   }
 }
 
-int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_proposals,
-                      int32_t n_leapfrog, const double* step_size_host, int32_t schedule_len, int32_t mass_kind,
-                      double mass_scalar, const float* mass_vec, int32_t rng_mode, uint64_t seed, uint64_t offset,
-                      const float* noise_p, const float* noise_u, float* traj, int32_t thin, int32_t* accept_count,
-                      float* energy_out, void* stream) {
+static int hmc_burst_impl(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_proposals,
+                          int32_t n_leapfrog, const double* step_size_host, int32_t schedule_len, int32_t mass_kind,
+                          double mass_scalar, const float* mass_vec, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                          const float* noise_p, const float* noise_u, float* traj, int32_t thin, int32_t* accept_count,
+                          float* energy_out, void* stream, const HmcDiag* diag) {
   int rc = validate_desc(e);
   if (rc) return rc;
   EBM_CHECK_ARG(x_in && x_out && n > 0, "x_in/x_out must be non-null and n positive");
@@ -168,7 +190,7 @@ int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, i
   P.n = n; P.d = e->dim; P.n_leapfrog = n_leapfrog; P.thin = thin; P.n_kept = n_proposals / thin;
   rc = make_mass(mass_kind, mass_scalar, mass_vec, P.mass);
   if (rc) return rc;
-  HmcCall c{e, step_size_host, schedule_len, n_proposals, offset, 0, 0, (cudaStream_t)stream};
+  HmcCall c{e, step_size_host, schedule_len, n_proposals, offset, 0, 0, (cudaStream_t)stream, diag};
   P.rng_p.mode = P.rng_u.mode = rng_mode;
   if (rng_mode == EBM_RNG_TORCH) {
     const long long numel = (long long)n * e->dim;
@@ -204,6 +226,38 @@ int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, i
       return hmc_chunks(c, P, [&](HmcParams& Pc, const HStepTable& tab) -> int { return hmc_mlp_launch(e, Pc, tab, c.st); });
     default: set_error("hmc: energy kind %d has no fused kernel", e->kind); return EBM_ERR_UNSUPPORTED;
   }
+}
+
+int ebm_hmc_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_proposals,
+                      int32_t n_leapfrog, const double* step_size_host, int32_t schedule_len, int32_t mass_kind,
+                      double mass_scalar, const float* mass_vec, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                      const float* noise_p, const float* noise_u, float* traj, int32_t thin, int32_t* accept_count,
+                      float* energy_out, void* stream) {
+  return hmc_burst_impl(e, x_in, x_out, n, n_proposals, n_leapfrog, step_size_host, schedule_len, mass_kind, mass_scalar,
+                        mass_vec, rng_mode, seed, offset, noise_p, noise_u, traj, thin, accept_count, energy_out, stream,
+                        nullptr);
+}
+
+int ebm_hmc_burst_diag_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_proposals,
+                           int32_t n_leapfrog, const double* step_size_host, int32_t schedule_len, int32_t mass_kind,
+                           double mass_scalar, const float* mass_vec, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                           const float* noise_p, const float* noise_u, float* traj, int32_t thin, double* diag_ws,
+                           float* scratch, int32_t* accept_count, float* diag_mean, float* diag_var, float* diag_energy,
+                           float* diag_accept, void* stream) {
+  EBM_CHECK_ARG(e && e->dim > 0, "null energy descriptor");
+  EBM_CHECK_ARG(thin >= 1 && n_proposals / thin >= 1, "thin must be >= 1 and keep at least one sample");
+  EBM_CHECK_ARG(diag_ws && scratch && accept_count && diag_mean && diag_var && diag_energy && diag_accept,
+                "diagnostic outputs and scratch buffers must be non-null");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_kept = n_proposals / thin;
+  EBM_CUDA(cudaMemsetAsync(diag_ws, 0, (size_t)n_kept * diag_slot(e->dim) * sizeof(double), st));
+  EBM_CUDA(cudaMemsetAsync(accept_count, 0, (size_t)n_proposals * sizeof(int32_t), st));
+  HmcDiag dg{diag_ws, scratch};
+  int rc = hmc_burst_impl(e, x_in, x_out, n, n_proposals, n_leapfrog, step_size_host, schedule_len, mass_kind, mass_scalar,
+                          mass_vec, rng_mode, seed, offset, noise_p, noise_u, traj, thin, accept_count, nullptr, stream, &dg);
+  if (rc) return rc;
+  return diag_finalize(diag_ws, n_kept, e->dim, n, 1.0f, 0.0f, diag_mean, diag_var, diag_energy, accept_count, thin,
+                       diag_accept, st);
 }
 
 }  // extern "C"

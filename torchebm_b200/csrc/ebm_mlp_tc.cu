@@ -36,6 +36,11 @@ constexpr int kTcRoleWarps = 4;          // one warpgroup: warp 0 issues the MMA
 constexpr int kTcThreads = 32 * (kTcRoleWarps + kTcEpiWarps);
 // 640 threads launch with 96 registers each; optionally the role warpgroup shrinks and the four epilogue warpgroups grow
 // (e.g. 128 * 32 + 512 * 112 = 640 * 96)
+// EBM_TC_LD32: 1 = every epilogue fetches its 32 accumulator columns with one tcgen05.ld and one wait, 0 = two 16-column
+// loads, each waited for where it is used
+#ifndef EBM_TC_LD32
+#define EBM_TC_LD32 1
+#endif
 #ifndef EBM_TC_ROLE_REGS
 // measured on B200 (tools/mlp_probe.py): 96/96 (no rebalance) 14.95 us per tile-step, 56/104 15.3, 32/112 15.9 -- here the
 // issue latency of the MMA thread matters more than the epilogue's few spills, so the default leaves the budget alone
@@ -60,6 +65,7 @@ struct TcParams {
   int n_steps, thin, n_kept, step_base, has_clamp;   // step_base: steps of this burst done by earlier launches
   float clamp_lo, clamp_hi;
   RowRng rng;
+  PhiloxKeys keys;    // round keys of (rng.k0, rng.k1)
   MlpSchedule sched;  // balanced (tile, step-range) split, mlp_schedule.cuh
 };
 
@@ -143,23 +149,144 @@ __device__ __forceinline__ void signal_cols(uint8_t* smem, int first_chunk, int 
   }
 }
 
+// ---- packed (fp32x2) epilogue arithmetic: the epilogue is bound by instruction issue (f32x2.cuh) --------------------
+// bf16 hi/lo split of a packed pair of activations; returns the two bf16x2 words (low half = first element).
+// With a lo part the hi part is the TRUNCATED value (one byte permute for the pair instead of a convert and a shift):
+// the residual v - hi is exact either way and is rounded to bf16; the weights stay split by rounding, so the dropped
+// lo*lo term remains unbiased (~2^-18 relative).  Without a lo part (single-pass bf16) hi is rounded to nearest.
+__device__ __forceinline__ void split2(f32x2 V, uint32_t& hi, uint32_t& lo, bool with_lo) {
+  float a, b;
+  unpack2(V, a, b);
+  if (with_lo) {
+    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+    hi = __byte_perm(ua, ub, 0x7632);
+    const f32x2 R = fma2(pack2(__uint_as_float(ua & 0xffff0000u), __uint_as_float(ub & 0xffff0000u)), -1.0f, V);   // exact
+    float ra, rb;
+    unpack2(R, ra, rb);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+  } else {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+}
+// 16 consecutive columns (8 pairs) of row r of the A operand, hi (and lo) copies
+__device__ __forceinline__ void store_a_16p(uint8_t* smem, int r, int col0, const f32x2* v, bool with_lo) {
+#pragma unroll
+  for (int oct = 0; oct < 2; ++oct) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[oct * 4 + j], ph[j], pl[j], with_lo);
+    const int off = core_offset(r, col0 + oct * 8, kTcM);
+    *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(smem + TcSmemLayout::a_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+// TMEM <-> 8 packed pairs (16 consecutive fp32 columns of this thread's lane)
+__device__ __forceinline__ void tmem_ld16p_nowait(uint32_t taddr, f32x2 (&v)[8]) {
+  asm volatile(
+      "{\n\t.reg .b32 r<16>;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15}, [%8];\n\t"
+      "mov.b64 %0, {r0, r1};\n\tmov.b64 %1, {r2, r3};\n\tmov.b64 %2, {r4, r5};\n\tmov.b64 %3, {r6, r7};\n\t"
+      "mov.b64 %4, {r8, r9};\n\tmov.b64 %5, {r10, r11};\n\tmov.b64 %6, {r12, r13};\n\tmov.b64 %7, {r14, r15};\n\t}\n"
+      : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]), "=l"(v[4]), "=l"(v[5]), "=l"(v[6]), "=l"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, f32x2 (&v)[8]) {
+  // the wait must sit between the load and the first use of its registers: keep load + wait in one asm block
+  asm volatile(
+      "{\n\t.reg .b32 r<16>;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15}, [%8];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "mov.b64 %0, {r0, r1};\n\tmov.b64 %1, {r2, r3};\n\tmov.b64 %2, {r4, r5};\n\tmov.b64 %3, {r6, r7};\n\t"
+      "mov.b64 %4, {r8, r9};\n\tmov.b64 %5, {r10, r11};\n\tmov.b64 %6, {r12, r13};\n\tmov.b64 %7, {r14, r15};\n\t}\n"
+      : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]), "=l"(v[4]), "=l"(v[5]), "=l"(v[6]), "=l"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 columns (16 pairs) in one instruction
+#define EBM_R32 "r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15, r16, r17, r18, r19, r20, r21, r22, r23, r24, r25, r26, r27, r28, r29, r30, r31"
+#define EBM_MOV32                                                                                                     \
+  "mov.b64 %0, {r0, r1};\n\tmov.b64 %1, {r2, r3};\n\tmov.b64 %2, {r4, r5};\n\tmov.b64 %3, {r6, r7};\n\t"               \
+  "mov.b64 %4, {r8, r9};\n\tmov.b64 %5, {r10, r11};\n\tmov.b64 %6, {r12, r13};\n\tmov.b64 %7, {r14, r15};\n\t"         \
+  "mov.b64 %8, {r16, r17};\n\tmov.b64 %9, {r18, r19};\n\tmov.b64 %10, {r20, r21};\n\tmov.b64 %11, {r22, r23};\n\t"     \
+  "mov.b64 %12, {r24, r25};\n\tmov.b64 %13, {r26, r27};\n\tmov.b64 %14, {r28, r29};\n\tmov.b64 %15, {r30, r31};\n\t"
+#define EBM_OUT32                                                                                                     \
+  "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]), "=l"(v[4]), "=l"(v[5]), "=l"(v[6]), "=l"(v[7]), "=l"(v[8]), "=l"(v[9]), \
+      "=l"(v[10]), "=l"(v[11]), "=l"(v[12]), "=l"(v[13]), "=l"(v[14]), "=l"(v[15])
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, f32x2 (&v)[16]) {
+  asm volatile("{\n\t.reg .b32 r<32>;\n\ttcgen05.ld.sync.aligned.32x32b.x32.b32 {" EBM_R32 "}, [%16];\n\t"
+               "tcgen05.wait::ld.sync.aligned;\n\t" EBM_MOV32 "}\n"
+               : EBM_OUT32
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32p_nowait(uint32_t taddr, f32x2 (&v)[16]) {
+  asm volatile("{\n\t.reg .b32 r<32>;\n\ttcgen05.ld.sync.aligned.32x32b.x32.b32 {" EBM_R32 "}, [%16];\n\t" EBM_MOV32 "}\n"
+               : EBM_OUT32
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const f32x2 (&v)[8]) {
+  asm volatile(
+      "{\n\t.reg .b32 r<16>;\n\t"
+      "mov.b64 {r0, r1}, %1;\n\tmov.b64 {r2, r3}, %2;\n\tmov.b64 {r4, r5}, %3;\n\tmov.b64 {r6, r7}, %4;\n\t"
+      "mov.b64 {r8, r9}, %5;\n\tmov.b64 {r10, r11}, %6;\n\tmov.b64 {r12, r13}, %7;\n\tmov.b64 {r14, r15}, %8;\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15};\n\t}\n"
+      :: "r"(taddr), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]), "l"(v[4]), "l"(v[5]), "l"(v[6]), "l"(v[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8p(uint32_t taddr, const f32x2 (&v)[4]) {
+  asm volatile(
+      "{\n\t.reg .b32 r<8>;\n\t"
+      "mov.b64 {r0, r1}, %1;\n\tmov.b64 {r2, r3}, %2;\n\tmov.b64 {r4, r5}, %3;\n\tmov.b64 {r6, r7}, %4;\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {r0, r1, r2, r3, r4, r5, r6, r7};\n\t}\n"
+      :: "r"(taddr), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3])
+      : "memory");
+}
+
+// activation and derivative of a packed pair; SiLU is fully packed (2 ex2 + 2 rcp + 6 packed ops per pair), the others
+// go through the scalar form
+template <int ACT>
+__device__ __forceinline__ void act_fast(float z, float& h, float& dh);
+template <int ACT>
+__device__ __forceinline__ void act2(f32x2 Z, f32x2& H, f32x2& DH) {
+  if (ACT == EBM_ACT_SILU) {
+    float t0, t1;
+    unpack2(mul2(Z, -1.4426950408889634f), t0, t1);
+    float d0, d1;
+    unpack2(add2(pack2(ex2_ftz(t0), ex2_ftz(t1)), 1.0f), d0, d1);
+    const f32x2 S = pack2(rcp_ftz(d0), rcp_ftz(d1));
+    H = mul2(Z, S);
+    DH = fma2(H, fma2(S, -1.0f, 1.0f), S);   // s + z s (1 - s)
+  } else {
+    float z0, z1, h0, h1, g0, g1;
+    unpack2(Z, z0, z1);
+    act_fast<ACT>(z0, h0, g0);
+    act_fast<ACT>(z1, h1, g1);
+    H = pack2(h0, h1);
+    DH = pack2(g0, g1);
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void act_fast(float z, float& h, float& dh) {
   if (ACT == EBM_ACT_SILU) {
-    const float s = rcp_fast(1.0f + __expf(-z));
+    const float s = rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * z));
     h = z * s;
     dh = s * (1.0f + z * (1.0f - s));
   } else if (ACT == EBM_ACT_TANH) {
-    const float e = __expf(-2.0f * fabsf(z));
-    const float t = copysignf((1.0f - e) * rcp_fast(1.0f + e), z);
+    const float e = ex2_ftz(-2.8853900817779268f * fabsf(z));
+    const float t = copysignf((1.0f - e) * rcp_ftz(1.0f + e), z);
     h = t;
     dh = 1.0f - t * t;
   } else if (ACT == EBM_ACT_RELU) {
     h = z > 0.0f ? z : 0.0f;
     dh = z > 0.0f ? 1.0f : 0.0f;
   } else {
-    h = z > 20.0f ? z : log1pf(__expf(z));
-    dh = rcp_fast(1.0f + __expf(-z));
+    h = z > 20.0f ? z : log1pf(ex2_ftz(1.4426950408889634f * z));
+    dh = rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * z));
   }
 }
 
@@ -217,7 +344,38 @@ __device__ __forceinline__ void tc_issue_gemm(uint8_t* smem, uint32_t tmem_d, in
   mma_commit(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8));
 }
 
-template <int ACT>
+// a thread's 32 consecutive columns of one row <-> global memory: eight 128-bit accesses when the row is 16-byte aligned
+// and lies inside the state, scalar otherwise
+__device__ __forceinline__ void tc_store_row32(float* __restrict__ dst, long long grow, int d, int col_base, bool rv,
+                                               const float (&x)[kTcCols]) {
+  if (!rv) return;
+  float* p = dst + grow * d + col_base;
+  if (col_base + kTcCols <= d && (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < kTcCols / 4; ++j)
+      reinterpret_cast<float4*>(p)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTcCols; ++i)
+      if (col_base + i < d) p[i] = x[i];
+  }
+}
+__device__ __forceinline__ void tc_load_row32(const float* __restrict__ src, long long grow, int d, int col_base, bool rv,
+                                              float (&x)[kTcCols]) {
+  const float* p = src + grow * d + col_base;
+  if (rv && col_base + kTcCols <= d && (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < kTcCols / 4; ++j) {
+      const float4 t = reinterpret_cast<const float4*>(p)[j];
+      x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTcCols; ++i) x[i] = (rv && col_base + i < d) ? p[i] : 0.0f;
+  }
+}
+
+template <int ACT, bool LO>
 __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __grid_constant__ TcParams P,
                                                                         const __grid_constant__ StepTable tab) {
   extern __shared__ __align__(128) uint8_t tc_smem_raw[];
@@ -256,6 +414,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     }
   } else {
     // ---- epilogue warps -------------------------------------------------------------------------
+    // Everything elementwise runs on packed fp32x2 pairs (pair j of a block = columns 2j, 2j+1).  Padded rows (>= n) and
+    // padded columns (>= d, h1, h2) are computed like real ones and never stored: the weights, biases and w3 are staged
+    // with zeros there, so they cannot leak into a real output, and they stay finite (a padded state column only
+    // accumulates noise).
     if (kTcEpiRegs > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
     const int e = warp - kTcRoleWarps;
     const int row = 32 * (warp & 3) + lane;        // TMEM lane this thread may access (hardware: warp % 4)
@@ -263,15 +425,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
     const int col_base = kTcCols * cq;
     const int first_chunk = col_base / 16;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + col_base;
-    const float* b1 = reinterpret_cast<const float*>(smem + TcSmemLayout::b1) + col_base;
-    const float* b2 = reinterpret_cast<const float*>(smem + TcSmemLayout::b2) + col_base;
-    const float* w3 = reinterpret_cast<const float*>(smem + TcSmemLayout::w3) + col_base;
+    const f32x2* b1 = reinterpret_cast<const f32x2*>(smem + TcSmemLayout::b1 + 4 * col_base);
+    const f32x2* b2 = reinterpret_cast<const f32x2*>(smem + TcSmemLayout::b2 + 4 * col_base);
+    const f32x2* w3 = reinterpret_cast<const f32x2*>(smem + TcSmemLayout::w3 + 4 * col_base);
     const uint32_t acc_bar = smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8);
-    const bool with_lo = P.passes == 3;
     const long long numel = P.n * P.d;
     const bool quad_rng = (P.d % 4 == 0);
     // NATIVE stream: the step's noise is drawn in four 8-column parts, one in front of each wait for a product, and
-    // parked in TMEM columns [384, 512) until the update epilogue -- the draw costs a quarter of the epilogue's
+    // parked in TMEM columns [384, 512) until the update epilogue -- the draw costs a third of the epilogue's
     // instructions and depends on nothing, so it fills the time the tensor pipe needs to finish each product
     const bool bubble_rng = (P.rng.mode == 2) && quad_rng;
     uint32_t parity = 0;
@@ -284,49 +445,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
       if (s0 > 0) mlp_unit_acquire(P.sched, kTcEpiWarps);
       const float* x0src = (s0 == 0) ? P.x_in : P.x_out;
       const long long row0 = (s0 == 0 && P.row_index && rv) ? P.row_index[grow] : grow;
-      float x[kTcCols];
+      f32x2 X[kTcCols / 2];
+      {
+        float xs[kTcCols];
+        tc_load_row32(x0src, row0, P.d, col_base, rv, xs);
 #pragma unroll
-      for (int i = 0; i < kTcCols; ++i) {
-        const int col = col_base + i;
-        x[i] = (rv && col < P.d) ? x0src[row0 * P.d + col] : 0.0f;
+        for (int j = 0; j < kTcCols / 2; ++j) X[j] = pack2(xs[2 * j], xs[2 * j + 1]);
       }
-      store_a_cols(smem, row, col_base, x, with_lo);
+      store_a_16p(smem, row, col_base, X, LO);
+      store_a_16p(smem, row, col_base + 16, X + 8, LO);
       signal_cols(smem, first_chunk, lane);
       int until_keep = P.thin - ((P.step_base + s0) % P.thin), kept = (P.step_base + s0) / P.thin;
-      RngStream rs;
-      rs.k0 = P.rng.k0; rs.k1 = P.rng.k1; rs.T = P.rng.T; rs.mode = P.rng.mode;
-      rs.ctr_base = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
+      unsigned long long ctr = P.rng.ctr_base + (unsigned long long)s0 * P.rng.ctr_step;
 
       auto draw_part = [&](int part) {
         if (!bubble_rng) return;
-        float e8[8];
+        f32x2 e8[4];
         const uint64_t q0 = (uint64_t)(grow * P.d + col_base + 8 * part) >> 2;
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {
           const uint64_t q = q0 + q4;
-          const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)rs.ctr_base, (uint32_t)(rs.ctr_base >> 32),
-                                        rs.k0, rs.k1);
-          const float4 nn = normal4_fast(w);
-          e8[4 * q4] = nn.x; e8[4 * q4 + 1] = nn.y; e8[4 * q4 + 2] = nn.z; e8[4 * q4 + 3] = nn.w;
+          const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), P.keys);
+          normal4_fast_packed(w, e8[2 * q4], e8[2 * q4 + 1]);
         }
-        tmem_st8(lane_addr + 384 + 8 * part, e8);
+        tmem_st8p(lane_addr + 384 + 8 * part, e8);
       };
 
       for (int k = s0; k < s1; ++k) {
         const int ti = k & tab.mask;
-        const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
+        const float h = tab.h[ti], c12 = tab.c1[ti] * tab.c2[ti];
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM columns [256, 384)
         draw_part(0);
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
+#if EBM_TC_LD32
+        f32x2 acc[16];
+        tmem_ld32p(lane_addr + 0, acc);
+#endif
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float v[16], s[16];
-          tmem_ld16(lane_addr + 0 + 16 * blk, v);
+          f32x2 sd[8];
+#if EBM_TC_LD32
+          f32x2* v = acc + 8 * blk;
+#else
+          f32x2 v[8];
+          tmem_ld16p(lane_addr + 0 + 16 * blk, v);
+#endif
 #pragma unroll
-          for (int i = 0; i < 16; ++i) act_fast<ACT>(v[i] + b1[16 * blk + i], v[i], s[i]);
-          tmem_st16(lane_addr + 256 + 16 * blk, s);
-          store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+          for (int j = 0; j < 8; ++j) act2<ACT>(add2(v[j], b1[8 * blk + j]), v[j], sd[j]);
+          tmem_st16p(lane_addr + 256 + 16 * blk, sd);
+          store_a_16p(smem, row, col_base + 16 * blk, &v[0], LO);
           tcgen05_fence_before();
           signal_one(smem, first_chunk + blk, lane);
         }
@@ -334,17 +502,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
         draw_part(1);
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
+#if EBM_TC_LD32
+        tmem_ld32p(lane_addr + 128, acc);
+#endif
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float v[16];
-          tmem_ld16(lane_addr + 128 + 16 * blk, v);
+#if EBM_TC_LD32
+          f32x2* v = acc + 8 * blk;
+#else
+          f32x2 v[8];
+          tmem_ld16p(lane_addr + 128 + 16 * blk, v);
+#endif
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float hh, dh;
-            act_fast<ACT>(v[i] + b2[16 * blk + i], hh, dh);
-            v[i] = w3[16 * blk + i] * dh;
+          for (int j = 0; j < 8; ++j) {
+            f32x2 hh, dh;
+            act2<ACT>(add2(v[j], b2[8 * blk + j]), hh, dh);
+            v[j] = mul2(dh, w3[8 * blk + j]);
           }
-          store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+          store_a_16p(smem, row, col_base + 16 * blk, &v[0], LO);
           tcgen05_fence_before();
           signal_one(smem, first_chunk + blk, lane);
         }
@@ -353,14 +528,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
         mbar_wait(acc_bar, parity); parity ^= 1;
         tcgen05_fence_after();
         tmem_st_wait();
+#if EBM_TC_LD32
+        tmem_ld32p_nowait(lane_addr + 0, acc);
+#endif
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float v[16], s[16];
-          tmem_ld16(lane_addr + 0 + 16 * blk, v);
-          tmem_ld16(lane_addr + 256 + 16 * blk, s);
+          f32x2 sd[8];
+#if EBM_TC_LD32
+          f32x2* v = acc + 8 * blk;
+#else
+          f32x2 v[8];
+          tmem_ld16p_nowait(lane_addr + 0 + 16 * blk, v);
+#endif
+          tmem_ld16p(lane_addr + 256 + 16 * blk, sd);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= s[i];
-          store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+          for (int j = 0; j < 8; ++j) v[j] = mul2(v[j], sd[j]);
+          store_a_16p(smem, row, col_base + 16 * blk, &v[0], LO);
           tcgen05_fence_before();
           signal_one(smem, first_chunk + blk, lane);
         }
@@ -372,53 +555,76 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
         const bool last = (k == s1 - 1);
         bool keep_now = false;
         if (P.traj && --until_keep == 0) { until_keep = P.thin; keep_now = kept < P.n_kept; ++kept; }
+#if EBM_TC_LD32
+        tmem_ld32p_nowait(lane_addr + 128, acc);
+#endif
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float g[16], eps[16];
+          f32x2 eps[8];
+#if EBM_TC_LD32
+          f32x2* g = acc + 8 * blk;
+#else
+          f32x2 g[8];
+#endif
           const int c0 = col_base + 16 * blk;
           const long long li0 = grow * P.d + c0;
           if (bubble_rng) {
-            tmem_ld16(lane_addr + 384 + 16 * blk, eps);
+            tmem_ld16p_nowait(lane_addr + 384 + 16 * blk, eps);
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool in = rv && (c0 + i) < P.d;
-              float ev = 0.0f;
-              if (in) ev = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i]
-                                             : normal_for_element_call(rs.k0, rs.k1, rs.ctr_base, rs.T, rs.mode, (uint64_t)(li0 + i));
-              eps[i] = ev;
+            for (int j = 0; j < 8; ++j) {
+              float ev[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int i = 2 * j + u;
+                const bool in = rv && (c0 + i) < P.d;
+                ev[u] = 0.0f;
+                if (in) ev[u] = (P.rng.mode == 0) ? P.noise[(long long)k * numel + li0 + i]
+                                                  : normal_for_element_call(P.rng.k0, P.rng.k1, ctr, P.rng.T, P.rng.mode, (uint64_t)(li0 + i));
+              }
+              eps[j] = pack2(ev[0], ev[1]);
             }
           }
-          tmem_ld16(lane_addr + 128 + 16 * blk, g);
+#if EBM_TC_LD32
+          tmem_ld_wait();
+#else
+          tmem_ld16p(lane_addr + 128 + 16 * blk, g);
+#endif
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x1 = __fsub_rn(x[16 * blk + i], __fmul_rn(h, g[i]));
-            float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
-            if (P.has_clamp) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
-            x[16 * blk + i] = (rv && (c0 + i) < P.d) ? xn : 0.0f;
+          for (int j = 0; j < 8; ++j) {
+            // x' = (x - h g) + c2 c1 eps (base_integrator.py:728-729; fused roundings are within this kernel's 2e-5 class)
+            f32x2 xn = fma2(eps[j], c12, fma2(g[j], -h, X[8 * blk + j]));
+            if (P.has_clamp) {
+              float a, b;
+              unpack2(xn, a, b);
+              xn = pack2(clamp_torch(a, P.clamp_lo, P.clamp_hi), clamp_torch(b, P.clamp_lo, P.clamp_hi));
+            }
+            X[8 * blk + j] = xn;
           }
           if (keep_now) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (rv && (c0 + i) < P.d) P.traj[(grow * P.n_kept + (kept - 1)) * P.d + c0 + i] = x[16 * blk + i];
+            for (int j = 0; j < 8; ++j) {
+              float a, b;
+              unpack2(X[8 * blk + j], a, b);
+              float* dst = P.traj + (grow * P.n_kept + (kept - 1)) * P.d + c0 + 2 * j;
+              if (rv && (c0 + 2 * j) < P.d) dst[0] = a;
+              if (rv && (c0 + 2 * j + 1) < P.d) dst[1] = b;
+            }
           }
           if (!last) {
-            store_a_16(smem, row, c0, x + 16 * blk, with_lo);
+            store_a_16p(smem, row, c0, X + 8 * blk, LO);
             tcgen05_fence_before();
             signal_one(smem, first_chunk + blk, lane);
           }
         }
-        rs.ctr_base += P.rng.ctr_step;
+        ctr += P.rng.ctr_step;
       }
-      if (rv) {
+      {
+        float xs[kTcCols];
 #pragma unroll
-        for (int i = 0; i < kTcCols; ++i)
-          if (col_base + i < P.d) P.x_out[grow * P.d + col_base + i] = x[i];
-        if (P.x_out2 && s1 == P.n_steps) {
-#pragma unroll
-          for (int i = 0; i < kTcCols; ++i)
-            if (col_base + i < P.d) P.x_out2[grow * P.d + col_base + i] = x[i];
-        }
+        for (int j = 0; j < kTcCols / 2; ++j) unpack2(X[j], xs[2 * j], xs[2 * j + 1]);
+        tc_store_row32(P.x_out, grow, P.d, col_base, rv, xs);
+        if (P.x_out2 && s1 == P.n_steps) tc_store_row32(P.x_out2, grow, P.d, col_base, rv, xs);
       }
       if (s1 < P.n_steps) mlp_unit_release(P.sched);  // the rest of this tile's burst runs on the next CTA
     }
@@ -442,37 +648,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
 // barrier per proposal) and every thread takes the Metropolis decision of its row.  The pre-proposal state is parked
 // in x_out.  Deviation from the reference in one corner: when safe-mode sanitising rewrites a NaN/inf coordinate the
 // reference recomputes the force at the sanitised state before the next step; here the carried force is kept.
-// a thread's 32 consecutive columns of one row <-> global memory: eight 128-bit accesses when the row is 16-byte aligned
-// and lies inside the state, scalar otherwise
-__device__ __forceinline__ void tc_store_row32(float* __restrict__ dst, long long grow, int d, int col_base, bool rv,
-                                               const float (&x)[kTcCols]) {
-  if (!rv) return;
-  float* p = dst + grow * d + col_base;
-  if (col_base + kTcCols <= d && (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-    for (int j = 0; j < kTcCols / 4; ++j)
-      reinterpret_cast<float4*>(p)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < kTcCols; ++i)
-      if (col_base + i < d) p[i] = x[i];
-  }
-}
-__device__ __forceinline__ void tc_load_row32(const float* __restrict__ src, long long grow, int d, int col_base, bool rv,
-                                              float (&x)[kTcCols]) {
-  const float* p = src + grow * d + col_base;
-  if (rv && col_base + kTcCols <= d && (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-#pragma unroll
-    for (int j = 0; j < kTcCols / 4; ++j) {
-      const float4 t = reinterpret_cast<const float4*>(p)[j];
-      x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < kTcCols; ++i) x[i] = (rv && col_base + i < d) ? p[i] : 0.0f;
-  }
-}
-
 struct TcHmcParams {
   TcParams T;      // weights, widths, passes, schedule; T.n_steps = proposals of this launch * (L + 1)
   HmcParams H;
@@ -837,6 +1012,7 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.rng.k0 = (uint32_t)c.seed ^ kNativeTag0; P.rng.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
     P.rng.ctr_step = 1;
   }
+  philox_expand_keys(P.keys, P.rng.k0, P.rng.k1);
   const long long tiles = (c.n + kTcM - 1) / kTcM;
   const int sms = (e->sm_margin > 0 && e->sm_margin < di.sm_count) ? di.sm_count - e->sm_margin : di.sm_count;
   const int grid = (int)(tiles < sms ? tiles : sms);
@@ -866,7 +1042,7 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     }
 #define CALL(A)                                                                                               \
   {                                                                                                           \
-    auto kern = langevin_mlp_tc_kernel<A>;                                                                    \
+    auto kern = passes == 3 ? langevin_mlp_tc_kernel<A, true> : langevin_mlp_tc_kernel<A, false>;             \
     EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmemLayout::total));   \
     kern<<<grid, kTcThreads, TcSmemLayout::total, c.st>>>(P, tab);                                            \
   }

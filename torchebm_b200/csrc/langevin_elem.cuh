@@ -9,6 +9,7 @@
 //   TORCH   : thread (t, j) owns li = t + T*(4j + ii), ii = 0..3  (torch's grid-stride quad)
 //   NATIVE / INJECTED : thread q owns li = 4q + ii                 (one float4)
 #pragma once
+#include "diag.cuh"
 #include "energies.cuh"
 #include "rng.cuh"
 
@@ -29,6 +30,7 @@ struct LangevinElemParams {
   float* x_out;
   const float* noise;  // INJECTED: [n_steps, numel]
   float* traj;         // [n, n_kept, d] or null
+  double* diag_ws;     // in-burst diagnostics workspace [n_kept, diag_slot(d)] or null (diag.cuh); TRAJ instantiations only
   long long numel;
   int d;
   int n_steps;
@@ -39,7 +41,7 @@ struct LangevinElemParams {
   int has_clamp;
   float clamp_lo, clamp_hi;
   // rng
-  uint32_t k0, k1;
+  PhiloxKeys keys;              // the ten Philox round keys of (k0, k1)
   unsigned long long ctr_base;  // TORCH: off/4 ; NATIVE: off/4
   unsigned long long ctr_step;  // TORCH: inc/4 per step ; NATIVE: 1 per step
   unsigned long long T;         // TORCH layout threads
@@ -56,12 +58,16 @@ struct LangevinElemParams {
 // HEUN: the two-stage tableau of integrators/heun.py through the reference's generic RK path
 // (core/base_integrator.py:300-347,387-397): k1 = f(x), k2 = f(x + h k1), x1 = x + h (k1/2 + k2/2), then the same noise.
 // The Heun instantiations always compile the clamp in (bounds = -inf / +inf when the sampler has none).
+//
+// The transform of the Philox words into normals runs on packed fp32x2 registers (rng.cuh), the update on scalar
+// ones; rounding order is the reference's x' = fl(fl(x - fl(h g)) + fl(c2 fl(eps c1))) (base_integrator.py:387-397,728-729).
 template <class EnergyT, int RNG, bool TRAJ, bool CLAMP, bool HEUN = false>
 __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constant__ LangevinElemParams P,
                                                             const EnergyT en,
                                                             const __grid_constant__ StepTable tab) {
   const unsigned long long gid = P.quad_base + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= P.quad_end) return;
+  const bool live = gid < P.quad_end;
+  if (!TRAJ && !live) return;    // (the keeping instantiations reduce over whole warps: idle threads stay, owning nothing)
 
   long long idx[4];
   uint32_t c2w, c3w;             // fixed counter words
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
 
   float x[4];
   bool ok[4];
-  const bool vec = (RNG != 1) && (idx[3] < P.numel) && ((reinterpret_cast<uintptr_t>(P.x_in) & 15) == 0);
+  const bool vec = live && (RNG != 1) && (idx[3] < P.numel) && ((reinterpret_cast<uintptr_t>(P.x_in) & 15) == 0);
   if (vec) {
     const float4 v = *reinterpret_cast<const float4*>(P.x_in + idx[0]);
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
@@ -92,64 +98,126 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ok[i] = idx[i] < P.numel;
+      ok[i] = live && idx[i] < P.numel;
       x[i] = ok[i] ? P.x_in[idx[i]] : 0.0f;
     }
   }
+  f32x2 X01 = pack2(x[0], x[1]), X23 = pack2(x[2], x[3]);
 
   long long tbase[4];
+  int tcol[4];
   if (TRAJ) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long r = idx[i] / P.d;
       const long long c = idx[i] - r * P.d;
       tbase[i] = r * (long long)P.n_kept * P.d + c;
+      tcol[i] = (int)c;
     }
   }
   int until_keep = P.thin_start;
   int kept = P.kept_base;
 
-  for (int k = 0; k < P.n_steps; ++k) {
-    const int ti = k & tab.mask;
-    const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
-    float e[4];
-    if (RNG == 0) {
-      const float* nz = P.noise + (long long)k * P.numel;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) e[i] = ok[i] ? nz[idx[i]] : 0.0f;
-    } else {
-      uint4 w;
-      if (RNG == 1) w = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), c2w, c3w, P.k0, P.k1);
-      else          w = philox4x32_10(c2w, c3w, (uint32_t)ctr, (uint32_t)(ctr >> 32), P.k0, P.k1);
-      ctr += P.ctr_step;
-      const float4 nrm = normal4(w);
-      e[0] = nrm.x; e[1] = nrm.y; e[2] = nrm.z; e[3] = nrm.w;
+  // One element pair: gradient, drift step, noise, clamp.
+  // Pipe facts (tools/pipe_probe.cu on B200, cycles per warp instruction per sub-partition): IMAD.WIDE 4.2, FFMA / FMUL
+  // 1.5, FFMA2 / FMUL2 2.1 (= 1.04 per element), LOP3 2.1 on another pipe, MUFU 8.  IMAD.WIDE, scalar and packed fp32
+  // all execute on the one FMA pipe, which is what this kernel is bound by: Philox's 20 IMAD.WIDE per thread-step are 83
+  // of its ~195 cycles.  Packing therefore buys pipe time only through the 1.04 vs 1.5 per element.
+  // TORCH / INJECTED streams: the reference's rounding order, every product and sum rounded separately (scalar ops).
+  // NATIVE stream: no bit-parity contract -- contracted packed form (5 packed instructions per pair instead of 18 scalar).
+  auto update2 = [&](f32x2 X, f32x2 E, float h, float c1s, float c2) -> f32x2 {
+    if (RNG == 2 && !HEUN) {
+      const f32x2 G = en.grad2_fast(X);
+      f32x2 XN = fma2(E, __fmul_rn(c1s, c2), fma2(G, -h, X));
+      if (CLAMP) {
+        float a, b;
+        unpack2(XN, a, b);
+        XN = pack2(clamp_torch(a, P.clamp_lo, P.clamp_hi), clamp_torch(b, P.clamp_lo, P.clamp_hi));
+      }
+      return XN;
     }
+    float xv[2], ev[2];
+    unpack2(X, xv[0], xv[1]);
+    unpack2(E, ev[0], ev[1]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float g = en.grad(x[i]);
+    for (int u = 0; u < 2; ++u) {
+      float g = en.grad(xv[u]);
       if (HEUN) {
-        const float g2 = en.grad(__fsub_rn(x[i], __fmul_rn(h, g)));
+        const float g2 = en.grad(__fsub_rn(xv[u], __fmul_rn(h, g)));
         g = __fadd_rn(__fmul_rn(0.5f, g), __fmul_rn(0.5f, g2));
       }
       // x1 = x + h*(1.0*(-g)) ; dw = eps*c1 ; x' = x1 + c2*dw   (base_integrator.py:387-397,728-729)
-      const float x1 = __fsub_rn(x[i], __fmul_rn(h, g));
-      float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(e[i], c1)));
+      const float x1 = __fsub_rn(xv[u], __fmul_rn(h, g));
+      float xn = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(ev[u], c1s)));
       if (CLAMP) xn = clamp_torch(xn, P.clamp_lo, P.clamp_hi);
-      x[i] = xn;
+      xv[u] = xn;
     }
+    return pack2(xv[0], xv[1]);
+  };
+
+  auto step = [&](int k, float h, float c1, float c2) {
+    f32x2 E01, E23;
+    float c1s = c1;
+    if (RNG == 0) {
+      const float* nz = P.noise + (long long)k * P.numel;
+      float e[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = ok[i] ? nz[idx[i]] : 0.0f;
+      E01 = pack2(e[0], e[1]);
+      E23 = pack2(e[2], e[3]);
+    } else if (RNG == 1) {
+      const uint4 w = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), c2w, c3w, P.keys);
+      ctr += P.ctr_step;
+      neg_normal4_packed(w, E01, E23);     // bit-identical to torch's curand_normal4, negated
+      c1s = -c1;
+    } else {
+      const uint4 w = philox4x32_10(c2w, c3w, (uint32_t)ctr, (uint32_t)(ctr >> 32), P.keys);
+      ctr += P.ctr_step;
+      normal4_fast_packed(w, E01, E23);    // the native stream pins the Philox words, not the transform's last bits
+    }
+    X01 = update2(X01, E01, h, c1s, c2);
+    X23 = update2(X23, E23, h, c1s, c2);
     if (TRAJ) {
       if (--until_keep == 0) {
         until_keep = P.thin;
         if (kept < P.n_kept) {
+          unpack2(X01, x[0], x[1]);
+          unpack2(X23, x[2], x[3]);
+          if (P.traj) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (ok[i]) P.traj[tbase[i] + (long long)kept * P.d] = x[i];
+            for (int i = 0; i < 4; ++i)
+              if (ok[i]) P.traj[tbase[i] + (long long)kept * P.d] = x[i];
+          }
+          if (P.diag_ws) {   // column sums and sums of squares, sum of the energy terms (diag.cuh)
+            double* slot = P.diag_ws + (long long)kept * diag_slot(P.d);
+            double es = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (ok[i]) {
+                const double xv = (double)x[i];
+                atomicAdd(slot + tcol[i], xv);
+                atomicAdd(slot + P.d + tcol[i], xv * xv);
+                es += (double)en.term(x[i]);
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(slot + 2 * P.d, es);
+          }
         }
         ++kept;
       }
     }
+  };
+
+  if (tab.mask == 0) {   // constant schedule: coefficients stay in registers
+    const float h = tab.h[0], c1 = tab.c1[0], c2 = tab.c2[0];
+    for (int k = 0; k < P.n_steps; ++k) step(k, h, c1, c2);
+  } else {
+    for (int k = 0; k < P.n_steps; ++k) step(k, tab.h[k], tab.c1[k], tab.c2[k]);
   }
+  unpack2(X01, x[0], x[1]);
+  unpack2(X23, x[2], x[3]);
 
   if (vec && ((reinterpret_cast<uintptr_t>(P.x_out) & 15) == 0)) {
     *reinterpret_cast<float4*>(P.x_out + idx[0]) = make_float4(x[0], x[1], x[2], x[3]);

@@ -62,7 +62,8 @@ class EulerMaruyamaIntegrator(BaseSDERungeKuttaIntegrator):
         if stochastic and noise is None:
             noise = torch.randn_like(x, generator=generator)
         fused = (x.is_cuda and x.dtype == torch.float32 and diffusion is None and not torch.is_tensor(step_size)
-                 and not torch.is_tensor(noise_scale))
+                 and not torch.is_tensor(noise_scale) and d.shape == x.shape and d.dtype == x.dtype
+                 and (noise is None or (noise.shape == x.shape and noise.dtype == x.dtype)))   # broadcastable-only drifts: eager
         if fused:
             return {"x": ops.euler_maruyama_step(x, d, noise, float(step_size),
                                                  None if noise_scale is None else float(noise_scale))}
@@ -148,6 +149,32 @@ class LeapfrogIntegrator(BaseSymplecticIntegrator):
 
 
 _REGISTRY = {"euler_maruyama": EulerMaruyamaIntegrator, "heun": HeunIntegrator, "leapfrog": LeapfrogIntegrator}
+
+# Integrator classes whose arithmetic the fused bursts reproduce: this package's and, when importable, the reference's
+# own (exact types only -- a subclass may override `step`).  dropin.py registers its reference-derived classes here.
+_EM_TYPES = {EulerMaruyamaIntegrator}
+_HEUN_TYPES = {HeunIntegrator}
+_LEAPFROG_TYPES = {LeapfrogIntegrator}
+
+
+def register_known_integrators(em=(), heun=(), leapfrog=()) -> None:
+    _EM_TYPES.update(em)
+    _HEUN_TYPES.update(heun)
+    _LEAPFROG_TYPES.update(leapfrog)
+
+
+def sde_scheme_of(integrator) -> Optional[str]:
+    """"euler_maruyama" / "heun" when `integrator` is one whose step the fused Langevin burst implements, else None."""
+    t = type(integrator)
+    if t in _EM_TYPES:
+        return "euler_maruyama"
+    if t in _HEUN_TYPES:
+        return "heun"
+    return None
+
+
+def is_plain_leapfrog(integrator) -> bool:
+    return type(integrator) in _LEAPFROG_TYPES
 
 
 def get_integrator(name: str, device=None, dtype=None) -> BaseIntegrator:

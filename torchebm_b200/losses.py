@@ -21,7 +21,119 @@ from . import ops
 from .core import TorchEBMModule
 
 
-class BaseContrastiveDivergence(TorchEBMModule):
+class FusedPCDMixin:
+    """Device-side replay-buffer logic shared by the standalone loss below and by the reference-derived one of dropin.py:
+    library kernels for the row gather + exploration noise and for the FIFO write-back, and the one-call negative
+    sampler.  Relies only on the attributes of core/base_loss.py:155-188 (`replay_buffer`, `buffer_ptr`,
+    `_buffer_ptr_int`, `buffer_size`, `new_sample_ratio`, `k_steps`, `sampler`, `persistent`, `buffer_initialized`)."""
+
+    # base_loss.py:266-337
+    def get_start_points(self, x: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        x = x.to(device=self.device, dtype=self.dtype)
+        batch_size = x.shape[0]
+        if not self.persistent:
+            return x.detach().clone()
+        if not self.buffer_initialized:
+            self.initialize_buffer(tuple(x.shape[1:]), generator=generator)
+            if not self.buffer_initialized:
+                raise RuntimeError("Buffer initialization failed.")
+        if not self.replay_buffer.is_cuda:
+            return self._get_start_points_unfused(x, generator)
+        indices = self._draw_start_indices(batch_size, generator)
+        noise_rows, noise = self._draw_exploration_noise(x, generator)
+        return ops.pcd_gather(self.replay_buffer, indices, noise_rows, noise)
+
+    def _draw_start_indices(self, batch_size: int, generator: Optional[torch.Generator]) -> torch.Tensor:
+        """base_loss.py:293-312: stratified start rows (uniform with replacement when the buffer is the smaller)."""
+        if self.buffer_size < batch_size:
+            warnings.warn(
+                f"Buffer size ({self.buffer_size}) is smaller than batch size ({batch_size}). Sampling with replacement.",
+                UserWarning)
+            return torch.randint(0, self.buffer_size, (batch_size,), device=self.device, generator=generator)
+        stride = self.buffer_size // batch_size
+        base = torch.arange(0, batch_size, device=self.device) * stride
+        offset = torch.randint(0, stride, (batch_size,), device=self.device, generator=generator)
+        return (base + offset) % self.buffer_size
+
+    def _draw_exploration_noise(self, x: torch.Tensor, generator: Optional[torch.Generator]):
+        """base_loss.py:317-332: the rows that get `+ 0.01 * randn` and that noise (same draws, same order)."""
+        if self.new_sample_ratio <= 0.0:
+            return None, None
+        batch_size = x.shape[0]
+        n_new = max(1, int(batch_size * self.new_sample_ratio))
+        noise_rows = torch.randperm(batch_size, device=self.device, generator=generator)[:n_new]
+        noise = torch.randn((n_new,) + tuple(x.shape[1:]), dtype=self.dtype, device=self.device, generator=generator)
+        return noise_rows, noise
+
+    def sample_negatives(self, x: torch.Tensor, model_kwargs: Optional[dict] = None,
+                         generator: Optional[torch.Generator] = None, energy_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The sampling half of `ContrastiveDivergence.forward` (contrastive_divergence.py:127-139): start points,
+        `k_steps` of the sampler, buffer write-back.  Same draws from `generator`, same buffer and pointer state as
+        `get_start_points` -> `sampler.sample` -> `update_buffer`; when the sampler offers `sample_from_buffer` and
+        nothing stands in the way (2-D state, no conditioning) the three steps are ONE library call: exploration noise
+        included, and with `buffer_size == batch` the burst kernel reads its start rows straight from the replay buffer
+        and writes its final state straight back.  `energy_out[batch]` (optional) receives E(x-)."""
+        fused = getattr(self.sampler, "sample_from_buffer", None)
+        if self.persistent and fused is not None and not model_kwargs and x.ndim == 2:
+            x = x.to(device=self.device, dtype=self.dtype)
+            if not self.buffer_initialized:
+                self.initialize_buffer(tuple(x.shape[1:]), generator=generator)
+                if not self.buffer_initialized:
+                    raise RuntimeError("Buffer initialization failed.")
+            if self.replay_buffer.is_cuda and self.replay_buffer.is_contiguous() and self.replay_buffer.dtype == torch.float32:
+                batch = x.shape[0]
+                indices = self._draw_start_indices(batch, generator)
+                noise_rows, noise = self._draw_exploration_noise(x, generator)
+                # buffer_size == batch: the stratified draw has stride 1, i.e. it is arange(batch) by construction
+                # (base_loss.py:307-312); the library takes its no-gather form only when told so explicitly (idx None)
+                identity = self.buffer_size == batch
+                res = fused(self.replay_buffer, None if identity else indices, self._buffer_ptr_int, self.k_steps,
+                            noise_rows=noise_rows, noise=noise, energy_out=energy_out, generator=generator)
+                if res is not None:
+                    pred, new_ptr = res
+                    self._buffer_ptr_int = new_ptr
+                    self.buffer_ptr.fill_(new_ptr)
+                    return pred
+                # nothing was consumed beyond the draws above: continue with the gathered start points
+                start_points = ops.pcd_gather(self.replay_buffer, indices, noise_rows, noise)
+                pred = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs, generator=generator)
+                with torch.no_grad():
+                    self.update_buffer(pred)
+                if energy_out is not None:
+                    with torch.no_grad():
+                        energy_out.copy_(self.model(pred))
+                return pred
+        start_points = self.get_start_points(x, generator=generator)
+        pred = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs, generator=generator)
+        if self.persistent:
+            with torch.no_grad():
+                self.update_buffer(pred)
+        if energy_out is not None:
+            with torch.no_grad():
+                energy_out.copy_(self.model(pred, **(model_kwargs or {})))
+        return pred
+
+    # base_loss.py:390-426
+    def update_buffer(self, samples: torch.Tensor) -> None:
+        if not self.persistent or not self.buffer_initialized:
+            return
+        if not self.replay_buffer.is_cuda:
+            return self._update_buffer_unfused(samples)
+        samples = samples.to(device=self.device, dtype=self.dtype).detach()
+        new_ptr = ops.pcd_scatter(self.replay_buffer, self._buffer_ptr_int, samples)
+        self._buffer_ptr_int = new_ptr
+        self.buffer_ptr.fill_(new_ptr)
+
+    # hooks for buffers that are not on a CUDA device: the standalone loss has no such path, dropin.py hands them to
+    # the reference's own implementation
+    def _get_start_points_unfused(self, x, generator):
+        raise RuntimeError("the persistent-CD buffer must live on a CUDA device: torchebm_b200 has no CPU path")
+
+    def _update_buffer_unfused(self, samples):
+        raise RuntimeError("the persistent-CD buffer must live on a CUDA device: torchebm_b200 has no CPU path")
+
+
+class BaseContrastiveDivergence(FusedPCDMixin, TorchEBMModule):
     def __init__(self, model, sampler, k_steps: int = 1, persistent: bool = False, buffer_size: int = 100,
                  new_sample_ratio: float = 0.0, init_steps: int = 0, dtype: torch.dtype = torch.float32,
                  device: Optional[Union[str, torch.device]] = None, *args, **kwargs):
@@ -65,82 +177,6 @@ class BaseContrastiveDivergence(TorchEBMModule):
         self._buffer_ptr_int = 0
         self.buffer_initialized = True
         return self.replay_buffer
-
-    # base_loss.py:266-337
-    def get_start_points(self, x: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        x = x.to(device=self.device, dtype=self.dtype)
-        batch_size = x.shape[0]
-        if not self.persistent:
-            return x.detach().clone()
-        if not self.buffer_initialized:
-            self.initialize_buffer(tuple(x.shape[1:]), generator=generator)
-            if not self.buffer_initialized:
-                raise RuntimeError("Buffer initialization failed.")
-        indices = self._draw_start_indices(batch_size, generator)
-        noise_rows = noise = None
-        if self.new_sample_ratio > 0.0:
-            n_new = max(1, int(batch_size * self.new_sample_ratio))
-            noise_rows = torch.randperm(batch_size, device=self.device, generator=generator)[:n_new]
-            noise = torch.randn((n_new,) + tuple(x.shape[1:]), dtype=self.dtype, device=self.device, generator=generator)
-        if self.replay_buffer.is_cuda:
-            return ops.pcd_gather(self.replay_buffer, indices, noise_rows, noise)
-        raise RuntimeError("the persistent-CD buffer must live on a CUDA device: torchebm_b200 has no CPU path")
-
-    def _draw_start_indices(self, batch_size: int, generator: Optional[torch.Generator]) -> torch.Tensor:
-        """base_loss.py:293-312: stratified start rows (uniform with replacement when the buffer is the smaller)."""
-        if self.buffer_size < batch_size:
-            warnings.warn(
-                f"Buffer size ({self.buffer_size}) is smaller than batch size ({batch_size}). Sampling with replacement.",
-                UserWarning)
-            return torch.randint(0, self.buffer_size, (batch_size,), device=self.device, generator=generator)
-        stride = self.buffer_size // batch_size
-        base = torch.arange(0, batch_size, device=self.device) * stride
-        offset = torch.randint(0, stride, (batch_size,), device=self.device, generator=generator)
-        return (base + offset) % self.buffer_size
-
-    def sample_negatives(self, x: torch.Tensor, model_kwargs: Optional[dict] = None,
-                         generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """The sampling half of `ContrastiveDivergence.forward` (contrastive_divergence.py:127-139): start points,
-        `k_steps` of the sampler, buffer write-back.  Same draws from `generator`, same buffer and pointer state as
-        `get_start_points` -> `sampler.sample` -> `update_buffer`; when the sampler offers `sample_from_buffer` and
-        nothing stands in the way (2-D state, no exploration noise, no conditioning) the three steps are one library
-        call that reads the start rows straight from the replay buffer and writes the final state straight back."""
-        fused = getattr(self.sampler, "sample_from_buffer", None)
-        if (self.persistent and fused is not None and not model_kwargs and self.new_sample_ratio <= 0.0 and x.ndim == 2):
-            x = x.to(device=self.device, dtype=self.dtype)
-            if not self.buffer_initialized:
-                self.initialize_buffer(tuple(x.shape[1:]), generator=generator)
-                if not self.buffer_initialized:
-                    raise RuntimeError("Buffer initialization failed.")
-            if self.replay_buffer.is_cuda and self.replay_buffer.is_contiguous():
-                indices = self._draw_start_indices(x.shape[0], generator)
-                res = fused(self.replay_buffer, indices, self._buffer_ptr_int, self.k_steps, generator=generator)
-                if res is not None:
-                    pred, new_ptr = res
-                    self._buffer_ptr_int = new_ptr
-                    self.buffer_ptr.fill_(new_ptr)
-                    return pred
-                # nothing was consumed beyond the index draw: continue with the gathered start points
-                start_points = ops.pcd_gather(self.replay_buffer, indices)
-                pred = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs, generator=generator)
-                with torch.no_grad():
-                    self.update_buffer(pred)
-                return pred
-        start_points = self.get_start_points(x, generator=generator)
-        pred = self.sampler.sample(x=start_points, n_steps=self.k_steps, model_kwargs=model_kwargs, generator=generator)
-        if self.persistent:
-            with torch.no_grad():
-                self.update_buffer(pred)
-        return pred
-
-    # base_loss.py:390-426
-    def update_buffer(self, samples: torch.Tensor) -> None:
-        if not self.persistent or not self.buffer_initialized:
-            return
-        samples = samples.to(device=self.device, dtype=self.dtype).detach()
-        new_ptr = ops.pcd_scatter(self.replay_buffer, self._buffer_ptr_int, samples)
-        self._buffer_ptr_int = new_ptr
-        self.buffer_ptr.fill_(new_ptr)
 
     # base_loss.py:428-481
     def mix_buffer_across_ranks(self, process_group=None, generator: Optional[torch.Generator] = None) -> None:

@@ -92,9 +92,12 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
                    noise_scales: Sequence[float], *, clamp: Optional[Tuple[float, float]] = None,
                    rng_mode: int = _lib.RNG_TORCH, seed: int = 0, offset: int = 0,
                    noise: Optional[torch.Tensor] = None, traj: Optional[torch.Tensor] = None, thin: int = 1,
-                   out: Optional[torch.Tensor] = None, scheme: str = "euler_maruyama") -> torch.Tensor:
-    """K-step burst (`scheme`: "euler_maruyama" or, for the elementwise energies, "heun").  `step_sizes` / `noise_scales` have length 1 (constant) or n_steps.  Returns the final
-    state (a new tensor unless `out` is given; `out` may be `x` for an in-place burst)."""
+                   out: Optional[torch.Tensor] = None, scheme: str = "euler_maruyama",
+                   diag: Optional[dict] = None) -> torch.Tensor:
+    """K-step burst (`scheme`: "euler_maruyama" or, for the elementwise energies, "heun").  `step_sizes` / `noise_scales`
+    have length 1 (constant) or n_steps.  Returns the final state (a new tensor unless `out` is given; `out` may be `x`
+    for an in-place burst).  `diag`: dict of preallocated "mean" [n_kept, d], "var" [n_kept, d], "energy" [n_kept]
+    (langevin_dynamics.py:170-185) filled by the same call."""
     x = _req(x, "x")
     if out is None:
         out = torch.empty_like(x)
@@ -103,11 +106,22 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
     assert len(step_sizes) == len(noise_scales) and len(step_sizes) in (1, n_steps)
     hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
     cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
+    heun = scheme != "euler_maruyama"
     with torch.cuda.device(x.device):
-        fn = _lib.load().ebm_langevin_burst_f32 if scheme == "euler_maruyama" else _lib.load().ebm_langevin_heun_burst_f32
+        if diag is not None and n_steps // thin > 0:
+            ws = torch.empty((n_steps // thin) * (2 * desc.dim + 2), dtype=torch.float64, device=x.device)
+            scratch = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+            rc = _lib.load().ebm_langevin_burst_diag_f32(
+                C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs, ns, len(step_sizes), cl,
+                int(rng_mode), int(seed), int(offset), _ptr(noise), _ptr(traj), int(thin), 1 if heun else 0, ws.data_ptr(),
+                scratch.data_ptr(), diag["mean"].data_ptr(), diag["var"].data_ptr(), diag["energy"].data_ptr(),
+                _stream(x.device))
+            _lib.check(rc, "ebm_langevin_burst_diag_f32")
+            return out
+        fn = _lib.load().ebm_langevin_heun_burst_f32 if heun else _lib.load().ebm_langevin_burst_f32
         rc = fn(C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs, ns, len(step_sizes), cl,
                 int(rng_mode), int(seed), int(offset), _ptr(noise), _ptr(traj), int(thin), _stream(x.device))
-    _lib.check(rc, "ebm_langevin_burst_f32" if scheme == "euler_maruyama" else "ebm_langevin_heun_burst_f32")
+    _lib.check(rc, "ebm_langevin_heun_burst_f32" if heun else "ebm_langevin_burst_f32")
     return out
 
 
@@ -186,7 +200,10 @@ def hmc_burst(desc: EnergyDescriptor, x: torch.Tensor, n_proposals: int, n_leapf
               *, mass=None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0, offset: int = 0,
               noise_p: Optional[torch.Tensor] = None, noise_u: Optional[torch.Tensor] = None,
               traj: Optional[torch.Tensor] = None, thin: int = 1, accept_count: Optional[torch.Tensor] = None,
-              energy_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              energy_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              diag: Optional[dict] = None) -> torch.Tensor:
+    """`diag`: dict of preallocated "mean" / "var" [n_kept, d], "energy" / "acceptance_rate" [n_kept] (hmc.py:294-310)
+    filled by the same call."""
     x = _req(x, "x")
     if out is None:
         out = torch.empty_like(x)
@@ -198,6 +215,18 @@ def hmc_burst(desc: EnergyDescriptor, x: torch.Tensor, n_proposals: int, n_leapf
     hs = _lib.doubles(list(step_sizes))
     kind, ms, mv = _mass_args(mass, x.device)
     with torch.cuda.device(x.device):
+        if diag is not None and n_proposals // thin > 0:
+            n_kept = n_proposals // thin
+            ws = torch.empty(n_kept * (2 * desc.dim + 2), dtype=torch.float64, device=x.device)
+            scratch = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+            acc = torch.empty(n_proposals, dtype=torch.int32, device=x.device)
+            rc = _lib.load().ebm_hmc_burst_diag_f32(
+                C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_proposals), int(n_leapfrog), hs,
+                len(step_sizes), kind, ms, _ptr(mv), int(rng_mode), int(seed), int(offset), _ptr(noise_p), _ptr(noise_u),
+                _ptr(traj), int(thin), ws.data_ptr(), scratch.data_ptr(), acc.data_ptr(), diag["mean"].data_ptr(),
+                diag["var"].data_ptr(), diag["energy"].data_ptr(), diag["acceptance_rate"].data_ptr(), _stream(x.device))
+            _lib.check(rc, "ebm_hmc_burst_diag_f32")
+            return out
         rc = _lib.load().ebm_hmc_burst_f32(
             C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_proposals), int(n_leapfrog), hs,
             len(step_sizes), kind, ms, _ptr(mv), int(rng_mode), int(seed), int(offset), _ptr(noise_p), _ptr(noise_u),
@@ -245,30 +274,44 @@ def pcd_langevin_fused(desc: EnergyDescriptor) -> bool:
     return bool(_lib.load().ebm_pcd_langevin_fused(C.byref(desc.c)))
 
 
-def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: torch.Tensor, ptr: int, n_steps: int,
+def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Optional[torch.Tensor], ptr: int, n_steps: int,
                        step_sizes: Sequence[float], noise_scales: Sequence[float], *,
                        clamp: Optional[Tuple[float, float]] = None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0,
-                       offset: int = 0) -> Tuple[torch.Tensor, int]:
-    """Start points `buffer[idx]` -> K-step burst -> FIFO write-back into `buffer` (in place).  Returns the negatives
-    and the new FIFO pointer (host int, no sync)."""
+                       offset: int = 0, noise_rows: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                       energy_out: Optional[torch.Tensor] = None, batch: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+    """Start points `buffer[idx]` (+ 0.01 * noise[j] on chain noise_rows[j]) -> K-step burst -> FIFO write-back into
+    `buffer` (in place).  `idx=None`: chain i starts from row i (`batch` chains, default the whole buffer) -- the
+    stride-1 case of core/base_loss.py:307-312.  Returns the negatives and the new FIFO pointer (host int, no sync);
+    `energy_out[n]` receives E(negatives)."""
     if not buffer.is_contiguous() or buffer.ndim != 2:
         raise ValueError("replay buffer must be a contiguous [S, D] tensor")
     buffer = _req(buffer, "buffer")
-    if idx.dtype != torch.int64 or not idx.is_cuda:
-        raise TypeError("idx must be a CUDA int64 tensor")
-    idx = idx.contiguous()
-    n = idx.shape[0]
+    if idx is not None:
+        if idx.dtype != torch.int64 or not idx.is_cuda:
+            raise TypeError("idx must be a CUDA int64 tensor")
+        idx = idx.contiguous()
+        n = idx.shape[0]
+    else:
+        n = buffer.shape[0] if batch is None else int(batch)
+    n_noise = 0
+    if noise_rows is not None:
+        if noise_rows.dtype != torch.int64 or not noise_rows.is_cuda:
+            raise TypeError("noise_rows must be a CUDA int64 tensor")
+        noise_rows = noise_rows.contiguous()
+        noise = _req(noise, "noise")
+        n_noise = noise_rows.shape[0]
     out = torch.empty((n, buffer.shape[1]), dtype=torch.float32, device=buffer.device)
-    scratch = None if pcd_langevin_fused(desc) else torch.empty_like(out)
+    reads_buffer = pcd_langevin_fused(desc) and ((idx is None and n == buffer.shape[0]) or (idx is not None and n_noise == 0))
+    scratch = None if reads_buffer else torch.empty_like(out)
     assert len(step_sizes) == len(noise_scales) and len(step_sizes) in (1, n_steps)
     hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
     cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
     new_ptr = C.c_int64(0)
     with torch.cuda.device(buffer.device):
         rc = _lib.load().ebm_pcd_langevin_burst_f32(
-            C.byref(desc.c), buffer.data_ptr(), buffer.shape[0], idx.data_ptr(), int(ptr), out.data_ptr(), _ptr(scratch), n,
-            int(n_steps), hs, ns, len(step_sizes), cl, int(rng_mode), int(seed), int(offset), C.byref(new_ptr),
-            _stream(buffer.device))
+            C.byref(desc.c), buffer.data_ptr(), buffer.shape[0], _ptr(idx), int(ptr), out.data_ptr(), _ptr(scratch), n,
+            int(n_steps), hs, ns, len(step_sizes), cl, int(rng_mode), int(seed), int(offset), _ptr(noise_rows), _ptr(noise),
+            n_noise, _ptr(energy_out), C.byref(new_ptr), _stream(buffer.device))
     _lib.check(rc, "ebm_pcd_langevin_burst_f32")
     return out, int(new_ptr.value)
 

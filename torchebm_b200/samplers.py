@@ -2,20 +2,24 @@
 
 Mirrors torchebm/core/base_sampler.py:10-155, torchebm/samplers/langevin_dynamics.py:16-188 and
 torchebm/samplers/hmc.py:19-315: same constructor and `sample()` signatures, same return shapes,
-same errors, same scheduler semantics, same RNG consumption (with `rng="torch"`, the default, a burst
+same errors, same scheduler semantics, same RNG consumption (with `rng = "torch"`, the default, a burst
 draws exactly the Philox stream the reference's per-step `randn_like` / `normal_` / `rand` calls would,
 so equal seeds give equal chains).  What differs is where the loop runs: one kernel launch does all
-`n_steps` steps (`thin` steps per launch when diagnostics are requested).
+`n_steps` steps, diagnostics included.
 
-Energies the library recognises (core.energy_descriptor) take the fused path.  Any other `nn.Module`
-energy keeps its own PyTorch forward/autograd for the gradient -- it is the caller's code -- and only the
-Euler-Maruyama update arithmetic runs in the library (the integrator-level boundary,
-core/base_integrator.py:673-731).  CPU tensors, non-fp32 dtypes and a missing CUDA library raise.
+The fused bodies live in mixins (`FusedLangevinMixin`, `FusedHMCMixin`, `FusedDescentMixin`) that are combined with
+one of two bases:
+  * this module's standalone classes (no reference package needed; requests outside the fused kernels' scope step
+    through the integrator-level path, and CPU tensors, non-fp32 dtypes or a missing CUDA library raise), or
+  * the reference's own classes when `torchebm` is importable (`torchebm_b200/dropin.py`): everything the fused path
+    does not cover is then handed to the reference's own `sample()` through `super()`.
+The mixin decides BEFORE it consumes any scheduler or generator state; `sampler.last_path` says which way the last call
+went ("fused" / "unfused").  `rng` ("torch" or "native") is an attribute, not a constructor argument: the constructor
+signatures are the reference's, `integrator` last (tests/samplers/test_api_contract.py:199-201).
 """
 
 from __future__ import annotations
 
-import warnings
 from abc import ABC, abstractmethod
 from typing import Any, Dict, Optional, Tuple, Union
 
@@ -23,9 +27,251 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from .core import BaseScheduler, EnergyDescriptor, Schedulable, TorchEBMModule, autograd_gradient, energy_descriptor
+from .core import (BaseScheduler, EnergyDescriptor, Schedulable, TorchEBMModule, advance_schedules, autograd_gradient,
+                   energy_descriptor)
 from .integrators import (BaseSDERungeKuttaIntegrator, BaseSymplecticIntegrator, EulerMaruyamaIntegrator,
-                          HeunIntegrator, LeapfrogIntegrator, resolve_integrator)
+                          HeunIntegrator, LeapfrogIntegrator, resolve_integrator, sde_scheme_of, is_plain_leapfrog)
+
+_ELEMENTWISE = ("double_well", "harmonic", "rastrigin")
+
+
+def _generator_state(device: torch.device, generator: Optional[torch.Generator]) -> Tuple[torch.Generator, int, int]:
+    """(generator, seed, offset) of the Philox stream a call draws from; no host sync."""
+    if generator is None:
+        generator = torch.cuda.default_generators[ops.device_index(device)]
+    elif generator.device.type != "cuda":
+        raise RuntimeError(f"Expected a 'cuda' device type for generator but found '{generator.device.type}'")
+    return generator, generator.initial_seed(), generator.get_offset()
+
+
+def _state_width(x, dim) -> Optional[int]:
+    """Row length of the 2-D state a call will run on, or None when the state is not [n, d]."""
+    if x is not None:
+        return int(x.shape[1]) if x.ndim == 2 else None
+    if dim is None:
+        return None
+    shape = (dim,) if isinstance(dim, int) else tuple(dim)
+    return int(shape[0]) if len(shape) == 1 else None
+
+
+class _RngAttribute:
+    """`sampler.rng`: "torch" (default; the reference's own Philox stream, equal seeds give equal chains) or "native"
+    (one Philox block per aligned quad of consecutive elements: cheaper, statistically equivalent)."""
+
+    _rng = "torch"
+
+    @property
+    def rng(self) -> str:
+        return self._rng
+
+    @rng.setter
+    def rng(self, value: str) -> None:
+        if value not in ("torch", "native"):
+            raise ValueError("rng must be 'torch' or 'native'")
+        object.__setattr__(self, "_rng", value)
+
+    def with_rng(self, value: str):
+        self.rng = value
+        return self
+
+
+def _batch_diag(x: torch.Tensor):
+    if x.shape[0] > 1:
+        return x.mean(dim=0), x.var(dim=0, unbiased=False).clamp_(min=1e-10, max=1e10)
+    return x.squeeze(0), torch.zeros_like(x.squeeze(0))
+
+
+# ======================================================================================================
+# fused bodies
+
+
+class FusedLangevinMixin(_RngAttribute):
+    """`sample()` of langevin_dynamics.py:82-188 as one fused burst."""
+
+    last_path: Optional[str] = None
+
+    def _fused_plan(self, x, dim, model_kwargs):
+        if self.device.type != "cuda" or self.dtype != torch.float32 or model_kwargs:
+            return None
+        d = _state_width(x, dim)
+        scheme = sde_scheme_of(self.integrator)
+        if d is None or scheme is None:
+            return None
+        desc = energy_descriptor(self.model, d, self.device)
+        if desc is None or (scheme == "heun" and desc.kind not in _ELEMENTWISE):
+            return None   # the fused Heun burst exists for the elementwise energies; others step through the integrator
+        return scheme, desc
+
+    @torch.no_grad()
+    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[Union[int, Tuple[int, ...]]] = None,
+               n_steps: int = 100, n_samples: int = 1, thin: int = 1, return_trajectory: bool = False,
+               return_diagnostics: bool = False, reset_schedulers: bool = True, *,
+               model_kwargs: Optional[Dict[str, Any]] = None, generator: Optional[torch.Generator] = None):
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        plan = self._fused_plan(x, dim, model_kwargs)
+        if plan is None or n_steps <= 0:
+            self.last_path = "unfused"
+            return self._sample_unfused(x, dim, n_steps, n_samples, thin, return_trajectory, return_diagnostics,
+                                        reset_schedulers, model_kwargs, generator)
+        scheme, desc = plan
+        _lib.load()   # a missing CUDA library is an error, never a reason to take another path
+        self.last_path = "fused"
+        if reset_schedulers:
+            self.reset_schedulers()
+        gen, seed, _ = _generator_state(self.device, generator)
+        x = self._init_state(x, dim, n_samples, generator).contiguous()
+        offset = gen.get_offset()  # after _init_state, which may have drawn from the same generator
+        n, data_shape = x.shape[0], x.shape[1:]
+        n_kept = n_steps // thin
+        rng_mode = _lib.RNG_MODES[self.rng]
+        traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
+        vals, _ = advance_schedules(self, ("step_size", "noise_scale"), n_steps)
+        diag = None
+        if return_diagnostics:
+            diag = {"mean": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
+                    "var": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
+                    "energy": torch.empty(n_kept, dtype=self.dtype, device=self.device)}
+        out = ops.langevin_burst(desc, x, n_steps, vals["step_size"], vals["noise_scale"], clamp=self.clamp,
+                                 rng_mode=rng_mode, seed=seed, offset=offset, traj=traj, thin=thin, scheme=scheme,
+                                 diag=diag)
+        gen.set_offset(offset + ops.rng_consumed_langevin(self.device, x.numel(), n_steps, rng_mode))
+        result = traj if return_trajectory else out
+        return (result, diag) if return_diagnostics else result
+
+    @torch.no_grad()
+    def sample_from_buffer(self, buffer: torch.Tensor, indices: Optional[torch.Tensor], ptr: int, n_steps: int, *,
+                           noise_rows: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                           energy_out: Optional[torch.Tensor] = None, reset_schedulers: bool = True,
+                           generator: Optional[torch.Generator] = None):
+        """Persistent-CD negatives in one library call: start points `buffer[indices]` (`indices=None`: row i for chain
+        i, the stride-1 case where the whole buffer is replaced) plus `0.01 * noise[j]` on row `noise_rows[j]`, `n_steps`
+        Langevin steps, FIFO write-back into `buffer` at `ptr` (get_start_points + sample + update_buffer of
+        core/base_loss.py:266-337,390-426 and losses/contrastive_divergence.py:127-139); `energy_out[n]` receives
+        E(x-) of the returned negatives.  Same scheduler and generator semantics as
+        `sample(x=start_points, n_steps=n_steps, generator=generator)`.  Returns `(negatives, new_ptr)`, or None when
+        this sampler / energy has no library kernel for it (the caller then takes the three-call path)."""
+        if sde_scheme_of(self.integrator) != "euler_maruyama" or buffer.ndim != 2 or not buffer.is_cuda:
+            return None   # (the one-call PCD path is Euler-Maruyama only)
+        if self.device.type != "cuda" or self.dtype != torch.float32:
+            return None
+        desc = energy_descriptor(self.model, buffer.shape[1], buffer.device)
+        if desc is None or n_steps <= 0:
+            return None
+        _lib.load()
+        if reset_schedulers:
+            self.reset_schedulers()
+        gen, seed, offset = _generator_state(self.device, generator)
+        rng_mode = _lib.RNG_MODES[self.rng]
+        vals, _ = advance_schedules(self, ("step_size", "noise_scale"), n_steps)
+        out, new_ptr = ops.pcd_langevin_burst(desc, buffer, indices, ptr, n_steps, vals["step_size"], vals["noise_scale"],
+                                              clamp=self.clamp, rng_mode=rng_mode, seed=seed, offset=offset,
+                                              noise_rows=noise_rows, noise=noise, energy_out=energy_out)
+        gen.set_offset(offset + ops.rng_consumed_langevin(self.device, out.numel(), n_steps, rng_mode))
+        return out, new_ptr
+
+
+class FusedHMCMixin(_RngAttribute):
+    """`sample()` of hmc.py:161-315 as one fused burst (all proposals of a call in one kernel)."""
+
+    last_path: Optional[str] = None
+
+    def _fused_plan(self, x, dim, model_kwargs):
+        if self.device.type != "cuda" or self.dtype != torch.float32 or model_kwargs:
+            return None
+        if not is_plain_leapfrog(self.integrator):
+            return None
+        if x is None and dim is None and hasattr(self.model, "mean") and isinstance(self.model.mean, torch.Tensor):
+            dim = self.model.mean.shape[0]
+        d = _state_width(x, dim)
+        if d is None:
+            return None
+        desc = energy_descriptor(self.model, d, self.device)
+        if desc is None:
+            return None
+        if desc.kind == "mlp" and (max(desc.c.dim, desc.c.hidden1, desc.c.hidden2) > 128
+                                   or desc.c.precision == _lib.MLP_BF16):
+            return None   # no fused HMC kernel: wider MLP energies, single-pass bf16 (accept tests want fp32-grade energies)
+        return desc, dim
+
+    @torch.no_grad()
+    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[int] = None, n_steps: int = 100,
+               n_samples: int = 1, thin: int = 1, return_trajectory: bool = False, return_diagnostics: bool = False,
+               reset_schedulers: bool = True, *, model_kwargs: Optional[Dict[str, Any]] = None,
+               generator: Optional[torch.Generator] = None):
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        plan = self._fused_plan(x, dim, model_kwargs)
+        if plan is None or n_steps <= 0:
+            self.last_path = "unfused"
+            return self._sample_unfused(x, dim, n_steps, n_samples, thin, return_trajectory, return_diagnostics,
+                                        reset_schedulers, model_kwargs, generator)
+        desc, dim = plan
+        _lib.load()
+        self.last_path = "fused"
+        if reset_schedulers:
+            self.reset_schedulers()
+        gen, seed, _ = _generator_state(self.device, generator)
+        x = self._init_state(x, dim, n_samples, generator).contiguous()
+        offset = gen.get_offset()
+        n, d = x.shape
+        n_kept = n_steps // thin
+        rng_mode = _lib.RNG_MODES[self.rng]
+        traj = torch.empty((n, n_kept, d), dtype=self.dtype, device=self.device) if return_trajectory else None
+        vals, _ = advance_schedules(self, ("step_size",), n_steps)
+        diag = None
+        if return_diagnostics:
+            diag = {k: torch.empty(n_kept, d, dtype=self.dtype, device=self.device) for k in ("mean", "var")}
+            diag["energy"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
+            diag["acceptance_rate"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
+        out = ops.hmc_burst(desc, x, n_steps, self.n_leapfrog_steps, vals["step_size"], mass=self.mass, rng_mode=rng_mode,
+                            seed=seed, offset=offset, traj=traj, thin=thin, diag=diag)
+        gen.set_offset(offset + ops.rng_consumed_hmc(self.device, n, d, n_steps, rng_mode))
+        result = traj if return_trajectory else out
+        return (result, diag) if return_diagnostics else result
+
+
+class FusedDescentMixin:
+    """`sample()` of samplers/gradient_descent.py:62-138,196-276 as one fused burst for the elementwise energies."""
+
+    last_path: Optional[str] = None
+
+    def _descent_momentum(self) -> Optional[float]:
+        return float(self.momentum) if hasattr(self, "momentum") else None
+
+    @torch.no_grad()
+    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[Union[int, Tuple[int, ...]]] = None,
+               n_steps: int = 100, n_samples: int = 1, thin: int = 1, return_trajectory: bool = False,
+               return_diagnostics: bool = False, reset_schedulers: bool = True, *,
+               model_kwargs: Optional[Dict[str, Any]] = None, generator: Optional[torch.Generator] = None):
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        desc = None
+        d = _state_width(x, dim)
+        if (self.device.type == "cuda" and self.dtype == torch.float32 and not model_kwargs and d is not None
+                and n_steps > 0 and not return_diagnostics):
+            desc = energy_descriptor(self.model, d, self.device)
+            if desc is not None and desc.kind not in _ELEMENTWISE:
+                desc = None
+        if desc is None:   # diagnostics need the energy of every kept state; other energies have no fused descent kernel
+            self.last_path = "unfused"
+            return self._sample_unfused(x, dim, n_steps, n_samples, thin, return_trajectory, return_diagnostics,
+                                        reset_schedulers, model_kwargs, generator)
+        _lib.load()
+        self.last_path = "fused"
+        if reset_schedulers:
+            self.reset_schedulers()
+        x = self._init_state(x, dim, n_samples, generator).contiguous()
+        n, data_shape = x.shape[0], x.shape[1:]
+        traj = (torch.empty((n, n_steps // thin, *data_shape), dtype=self.dtype, device=self.device)
+                if return_trajectory else None)
+        vals, _ = advance_schedules(self, ("step_size",), n_steps)
+        out = ops.descent_burst(desc, x, n_steps, vals["step_size"], momentum=self._descent_momentum(), traj=traj, thin=thin)
+        return traj if return_trajectory else out
+
+
+# ======================================================================================================
+# standalone bases (used when the reference package is not importable)
 
 
 class BaseSampler(Schedulable, TorchEBMModule, ABC):
@@ -56,8 +302,8 @@ class BaseSampler(Schedulable, TorchEBMModule, ABC):
             return self.model(x, **model_kwargs)
         return self.model(x)
 
-    # ---- fused-path plumbing ------------------------------------------------------------------
     def _require_cuda_fp32(self) -> None:
+        """The standalone classes have nothing to hand other devices / dtypes to (no reference package here)."""
         if self.device.type != "cuda":
             raise RuntimeError(
                 f"{type(self).__name__} runs on a CUDA device only (got device={self.device}); "
@@ -66,160 +312,46 @@ class BaseSampler(Schedulable, TorchEBMModule, ABC):
             raise TypeError(f"{type(self).__name__} supports dtype=torch.float32 only, got {self.dtype}")
         _lib.load()
 
-    def _rng_state(self, generator: Optional[torch.Generator]) -> Tuple[torch.Generator, int, int]:
-        """(generator, seed, offset) of the Philox stream this call draws from; no host sync."""
-        if generator is None:
-            idx = ops.device_index(self.device)
-            generator = torch.cuda.default_generators[idx]
-        elif generator.device.type != "cuda":
-            raise RuntimeError(
-                f"Expected a 'cuda' device type for generator but found '{generator.device.type}'")
-        return generator, generator.initial_seed(), generator.get_offset()
-
-    def _descriptor(self, x: torch.Tensor, model_kwargs: dict) -> Optional[EnergyDescriptor]:
-        if model_kwargs or x.ndim != 2:
-            return None
-        return energy_descriptor(self.model, x.shape[1], x.device)
-
     @abstractmethod
     def sample(self, x=None, dim=None, n_steps=100, n_samples=1, thin=1, return_trajectory=False,
                return_diagnostics=False, reset_schedulers=True, *, generator=None): ...
 
 
-def _batch_diag(x: torch.Tensor):
-    if x.shape[0] > 1:
-        return x.mean(dim=0), x.var(dim=0, unbiased=False).clamp_(min=1e-10, max=1e10)
-    return x.squeeze(0), torch.zeros_like(x.squeeze(0))
-
-
-class LangevinDynamics(BaseSampler):
-    """langevin_dynamics.py:16-188.  Extra keyword `rng`: "torch" (default, reference-identical stream) or
-    "native" (cheaper layout-native Philox stream)."""
+class _LangevinBase(BaseSampler):
+    """Constructor of langevin_dynamics.py:53-80 and, as `_sample_unfused`, its per-step loop (:157-185) through the
+    integrator-level boundary: energies with no library kernel keep their own gradient, the integrator runs the
+    library's fused update."""
 
     def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3,
                  noise_scale: Union[float, BaseScheduler] = 1.0, decay: float = 0.0,
                  clamp: Optional[Tuple[float, float]] = None, dtype: torch.dtype = torch.float32,
                  device: Optional[Union[str, torch.device]] = None,
-                 integrator: Union[str, BaseSDERungeKuttaIntegrator, None] = None, rng: str = "torch"):
+                 integrator: Union[str, BaseSDERungeKuttaIntegrator, None] = None):
         super().__init__(model=model, dtype=dtype, device=device)
         self._register_param("step_size", step_size, positive=True)
         self._register_param("noise_scale", noise_scale, positive=True)
         if clamp is not None and clamp[0] >= clamp[1]:
             raise ValueError(f"clamp min must be < max, got {clamp}")
-        if rng not in ("torch", "native"):
-            raise ValueError("rng must be 'torch' or 'native'")
         self.clamp = clamp
         self.decay = decay
-        self.rng = rng
         self.integrator = resolve_integrator(integrator, default="euler_maruyama", family=BaseSDERungeKuttaIntegrator,
                                              owner="LangevinDynamics", device=self.device, dtype=self.dtype)
 
-    @torch.no_grad()
-    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[Union[int, Tuple[int, ...]]] = None,
-               n_steps: int = 100, n_samples: int = 1, thin: int = 1, return_trajectory: bool = False,
-               return_diagnostics: bool = False, reset_schedulers: bool = True, *,
-               model_kwargs: Optional[Dict[str, Any]] = None, generator: Optional[torch.Generator] = None):
-        if thin < 1:
-            raise ValueError("thin must be >= 1")
+    def _sample_unfused(self, x, dim, n_steps, n_samples, thin, return_trajectory, return_diagnostics, reset_schedulers,
+                        model_kwargs, generator):
         self._require_cuda_fp32()
         if reset_schedulers:
             self.reset_schedulers()
-        gen, seed, offset = self._rng_state(generator)
         x = self._init_state(x, dim, n_samples, generator)
-        offset = gen.get_offset()  # after _init_state, which may have drawn from the same generator
         model_kwargs = self._prepare_model_kwargs(model_kwargs)
-        n = x.shape[0]
-        data_shape = x.shape[1:]
-        n_kept = n_steps // thin
-        scheme = {EulerMaruyamaIntegrator: "euler_maruyama", HeunIntegrator: "heun"}.get(type(self.integrator))
-        desc = self._descriptor(x, model_kwargs) if scheme is not None else None
-        if desc is not None and scheme == "heun" and desc.kind not in ("double_well", "harmonic", "rastrigin"):
-            desc = None   # the fused Heun burst exists for the elementwise energies; others step through the integrator
-        if desc is None:
-            return self._sample_opaque(x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator)
-
-        x = x.contiguous()
-        rng_mode = _lib.RNG_MODES[self.rng]
-        numel = x.numel()
-        traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
-        if n_steps <= 0:
-            out = traj if return_trajectory else x
-            return (out, self._empty_diag(data_shape)) if return_diagnostics else out
-        vals, constant = self._advance_schedules(("step_size", "noise_scale"), n_steps)
-        hs, nss = vals["step_size"], vals["noise_scale"]
-
-        if not return_diagnostics:
-            out = ops.langevin_burst(desc, x, n_steps, hs, nss, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
-                                     offset=offset, traj=traj, thin=thin, scheme=scheme)
-            gen.set_offset(offset + ops.rng_consumed_langevin(self.device, numel, n_steps, rng_mode))
-            return traj if return_trajectory else out
-
-        # diagnostics: one launch per kept sample, statistics from the device-resident state
-        diag = self._empty_diag(data_shape, n_kept)
-        cur = x
-        done = 0
-        for j in range(n_kept):
-            h_j = hs if constant else hs[done:done + thin]
-            ns_j = nss if constant else nss[done:done + thin]
-            cur = ops.langevin_burst(desc, cur, thin, h_j, ns_j, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
-                                     offset=offset, scheme=scheme)
-            offset += ops.rng_consumed_langevin(self.device, numel, thin, rng_mode)
-            done += thin
-            if traj is not None:
-                traj[:, j] = cur
-            diag["mean"][j], diag["var"][j] = _batch_diag(cur)
-            diag["energy"][j] = ops.energy(desc, cur).mean()
-        rest = n_steps - done
-        if rest > 0:
-            h_j = hs if constant else hs[done:]
-            ns_j = nss if constant else nss[done:]
-            cur = ops.langevin_burst(desc, cur, rest, h_j, ns_j, clamp=self.clamp, rng_mode=rng_mode, seed=seed,
-                                     offset=offset, scheme=scheme)
-            offset += ops.rng_consumed_langevin(self.device, numel, rest, rng_mode)
-        gen.set_offset(offset)
-        out = traj if return_trajectory else cur
-        return out, diag
-
-    @torch.no_grad()
-    def sample_from_buffer(self, buffer: torch.Tensor, indices: torch.Tensor, ptr: int, n_steps: int, *,
-                           reset_schedulers: bool = True, generator: Optional[torch.Generator] = None):
-        """Persistent-CD negatives in one library call: start points `buffer[indices]`, `n_steps` Langevin steps,
-        FIFO write-back into `buffer` at `ptr` (get_start_points + sample + update_buffer of
-        core/base_loss.py:266-337,390-426 and losses/contrastive_divergence.py:127-139, without exploration noise).
-        Same scheduler and generator semantics as `sample(x=buffer[indices], n_steps=n_steps, generator=generator)`.
-        Returns `(negatives, new_ptr)`, or None when this sampler / energy has no library kernel for it (the caller
-        then takes the three-call path)."""
-        if type(self.integrator) is not EulerMaruyamaIntegrator or buffer.ndim != 2 or not buffer.is_cuda:
-            return None   # (the one-call PCD path is Euler-Maruyama only)
-        self._require_cuda_fp32()
-        desc = energy_descriptor(self.model, buffer.shape[1], buffer.device)
-        if desc is None or n_steps <= 0:
-            return None
-        if reset_schedulers:
-            self.reset_schedulers()
-        gen, seed, offset = self._rng_state(generator)
-        rng_mode = _lib.RNG_MODES[self.rng]
-        vals, _ = self._advance_schedules(("step_size", "noise_scale"), n_steps)
-        out, new_ptr = ops.pcd_langevin_burst(desc, buffer, indices, ptr, n_steps, vals["step_size"], vals["noise_scale"],
-                                              clamp=self.clamp, rng_mode=rng_mode, seed=seed, offset=offset)
-        gen.set_offset(offset + ops.rng_consumed_langevin(self.device, out.numel(), n_steps, rng_mode))
-        return out, new_ptr
-
-    def _empty_diag(self, data_shape, n_kept: int = 0):
-        return {
-            "mean": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
-            "var": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
-            "energy": torch.empty(n_kept, dtype=self.dtype, device=self.device),
-        }
-
-    def _sample_opaque(self, x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator):
-        """Energies with no library kernel: their own gradient + the integrator's fused update per step
-        (langevin_dynamics.py:157-185 verbatim in structure)."""
-        n = x.shape[0]
-        data_shape = x.shape[1:]
+        n, data_shape = x.shape[0], x.shape[1:]
         n_kept = n_steps // thin
         traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
-        diag = self._empty_diag(data_shape, n_kept) if return_diagnostics else None
+        diag = None
+        if return_diagnostics:
+            diag = {"mean": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
+                    "var": torch.empty(n_kept, *data_shape, dtype=self.dtype, device=self.device),
+                    "energy": torch.empty(n_kept, dtype=self.dtype, device=self.device)}
         drift = lambda x_, t_: -self._model_gradient(x_, model_kwargs)
         keep = 0
         for i in range(n_steps):
@@ -240,102 +372,28 @@ class LangevinDynamics(BaseSampler):
         return (out, diag) if return_diagnostics else out
 
 
-class HamiltonianMonteCarlo(BaseSampler):
-    """hmc.py:19-315.  Extra keyword `rng` as in LangevinDynamics."""
+class LangevinDynamics(FusedLangevinMixin, _LangevinBase):
+    """langevin_dynamics.py:16-188."""
+
+
+class _HMCBase(BaseSampler):
+    """Constructor of hmc.py:55-90 and, as `_sample_unfused`, its proposal loop (:244-312) through the integrator."""
 
     def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3, n_leapfrog_steps: int = 10,
                  mass: Optional[Union[float, torch.Tensor]] = None, dtype: torch.dtype = torch.float32,
                  device: Optional[Union[str, torch.device]] = None,
-                 integrator: Union[str, BaseSymplecticIntegrator, None] = None, rng: str = "torch"):
+                 integrator: Union[str, BaseSymplecticIntegrator, None] = None):
         super().__init__(model=model, dtype=dtype, device=device)
         self._register_param("step_size", step_size, positive=True)
         if n_leapfrog_steps <= 0:
             raise ValueError("n_leapfrog_steps must be positive")
-        if rng not in ("torch", "native"):
-            raise ValueError("rng must be 'torch' or 'native'")
         self.n_leapfrog_steps = n_leapfrog_steps
         self.mass = mass.to(self.device) if (mass is not None and not isinstance(mass, float)) else mass
-        self.rng = rng
         integ = resolve_integrator(integrator, default="leapfrog", family=BaseSymplecticIntegrator,
                                    owner="HamiltonianMonteCarlo", device=self.device, dtype=self.dtype)
         if not integ.separable:
             raise TypeError("HamiltonianMonteCarlo requires a separable symplectic integrator")
         self.integrator = integ
-
-    @torch.no_grad()
-    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[int] = None, n_steps: int = 100,
-               n_samples: int = 1, thin: int = 1, return_trajectory: bool = False, return_diagnostics: bool = False,
-               reset_schedulers: bool = True, *, model_kwargs: Optional[Dict[str, Any]] = None,
-               generator: Optional[torch.Generator] = None):
-        if thin < 1:
-            raise ValueError("thin must be >= 1")
-        self._require_cuda_fp32()
-        if reset_schedulers:
-            self.reset_schedulers()
-        model_kwargs = self._prepare_model_kwargs(model_kwargs)
-        if x is None and dim is None:
-            if hasattr(self.model, "mean") and isinstance(self.model.mean, torch.Tensor):
-                dim = self.model.mean.shape[0]
-            else:
-                raise ValueError("dim must be provided when x is None and cannot be inferred from model")
-        gen, seed, _ = self._rng_state(generator)
-        x = self._init_state(x, dim, n_samples, generator)
-        offset = gen.get_offset()
-        if x.ndim != 2:
-            raise ValueError(f"HamiltonianMonteCarlo expects a 2-D state [n_samples, dim], got {tuple(x.shape)}")
-        n, d = x.shape
-        n_kept = n_steps // thin
-        desc = self._descriptor(x, model_kwargs) if type(self.integrator) is LeapfrogIntegrator else None
-        if desc is None or (desc.kind == "mlp" and max(desc.c.dim, desc.c.hidden1, desc.c.hidden2) > 128):
-            # no fused HMC kernel for this energy (custom models, MLP energies wider than 128, conditioning, custom
-            # symplectic integrators): the integrator-level path, hmc.py:244-312 step for step
-            return self._sample_opaque(x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator)
-        x = x.contiguous()
-        rng_mode = _lib.RNG_MODES[self.rng]
-        traj = torch.empty((n, n_kept, d), dtype=self.dtype, device=self.device) if return_trajectory else None
-        diag = None
-        if return_diagnostics:
-            diag = {k: torch.empty(n_kept, d, dtype=self.dtype, device=self.device) for k in ("mean", "var")}
-            diag["energy"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
-            diag["acceptance_rate"] = torch.empty(n_kept, dtype=self.dtype, device=self.device)
-        if n_steps <= 0:
-            out = traj if return_trajectory else x
-            return (out, diag) if return_diagnostics else out
-        vals, constant = self._advance_schedules(("step_size",), n_steps)
-        hs = vals["step_size"]
-
-        if not return_diagnostics:
-            out = ops.hmc_burst(desc, x, n_steps, self.n_leapfrog_steps, hs, mass=self.mass, rng_mode=rng_mode,
-                                seed=seed, offset=offset, traj=traj, thin=thin)
-            gen.set_offset(offset + ops.rng_consumed_hmc(self.device, n, d, n_steps, rng_mode))
-            return traj if return_trajectory else out
-
-        cur = x
-        done = 0
-        acc = torch.zeros(n_steps, dtype=torch.int32, device=self.device)
-        e_out = torch.empty(n, dtype=self.dtype, device=self.device)
-        for j in range(n_kept):
-            h_j = hs if constant else hs[done:done + thin]
-            cur = ops.hmc_burst(desc, cur, thin, self.n_leapfrog_steps, h_j, mass=self.mass, rng_mode=rng_mode,
-                                seed=seed, offset=offset, accept_count=acc[done:done + thin], energy_out=e_out)
-            offset += ops.rng_consumed_hmc(self.device, n, d, thin, rng_mode)
-            done += thin
-            if traj is not None:
-                traj[:, j, :] = cur
-            diag["mean"][j] = cur.mean(dim=0)
-            diag["var"][j] = (cur.var(dim=0, unbiased=False).clamp_(min=1e-10, max=1e10) if n > 1
-                              else torch.zeros(d, dtype=self.dtype, device=self.device))
-            diag["energy"][j] = e_out.mean()
-            diag["acceptance_rate"][j] = acc[done - 1].to(self.dtype) / n
-        rest = n_steps - done
-        if rest > 0:
-            h_j = hs if constant else hs[done:]
-            cur = ops.hmc_burst(desc, cur, rest, self.n_leapfrog_steps, h_j, mass=self.mass, rng_mode=rng_mode,
-                                seed=seed, offset=offset)
-            offset += ops.rng_consumed_hmc(self.device, n, d, rest, rng_mode)
-        gen.set_offset(offset)
-        out = traj if return_trajectory else cur
-        return out, diag
 
     def _kinetic(self, p: torch.Tensor) -> torch.Tensor:
         """hmc.py:136-159."""
@@ -345,10 +403,23 @@ class HamiltonianMonteCarlo(BaseSampler):
             return 0.5 * torch.sum(p.square(), dim=-1) / self.mass
         return 0.5 * torch.sum(p.square() / self.mass.view((1,) * (p.ndim - 1) + (-1,)), dim=-1)
 
-    def _sample_opaque(self, x, n_steps, thin, return_trajectory, return_diagnostics, model_kwargs, generator):
+    def _sample_unfused(self, x, dim, n_steps, n_samples, thin, return_trajectory, return_diagnostics, reset_schedulers,
+                        model_kwargs, generator):
         """Energies with no fused HMC kernel: their own energy / gradient (the library's MLP kernels when the model is
         an `MLPEnergy`, autograd otherwise) driven through the integrator, proposal by proposal, in the reference's
         order of operations and draws (hmc.py:244-312: `normal_` for the momentum, `rand(N)` for the accept test)."""
+        self._require_cuda_fp32()
+        if reset_schedulers:
+            self.reset_schedulers()
+        model_kwargs = self._prepare_model_kwargs(model_kwargs)
+        if x is None and dim is None:
+            if hasattr(self.model, "mean") and isinstance(self.model.mean, torch.Tensor):
+                dim = self.model.mean.shape[0]
+            else:
+                raise ValueError("dim must be provided when x is None and cannot be inferred from model")
+        x = self._init_state(x, dim, n_samples, generator)
+        if x.ndim != 2:
+            raise ValueError(f"HamiltonianMonteCarlo expects a 2-D state [n_samples, dim], got {tuple(x.shape)}")
         n, d = x.shape
         n_kept = n_steps // thin
         traj = torch.empty((n, n_kept, d), dtype=self.dtype, device=self.device) if return_trajectory else None
@@ -387,20 +458,16 @@ class HamiltonianMonteCarlo(BaseSampler):
         return (out, diag) if return_diagnostics else out
 
 
-class _DescentSampler(BaseSampler):
-    """Shared body of the noise-free samplers (samplers/gradient_descent.py:16-281): elementwise library energies run as
-    one fused burst (`ops.descent_burst`); every other energy steps through its own gradient (the library's kernels for
-    recognised energies, autograd otherwise) with the reference's ATen update ops."""
+class HamiltonianMonteCarlo(FusedHMCMixin, _HMCBase):
+    """hmc.py:19-315."""
 
-    _momentum: Optional[float] = None
 
-    @torch.no_grad()
-    def sample(self, x: Optional[torch.Tensor] = None, dim: Optional[Union[int, Tuple[int, ...]]] = None,
-               n_steps: int = 100, n_samples: int = 1, thin: int = 1, return_trajectory: bool = False,
-               return_diagnostics: bool = False, reset_schedulers: bool = True, *,
-               model_kwargs: Optional[Dict[str, Any]] = None, generator: Optional[torch.Generator] = None):
-        if thin < 1:
-            raise ValueError("thin must be >= 1")
+class _DescentBase(BaseSampler):
+    """Step-by-step loops of samplers/gradient_descent.py:123-138,258-276 with the reference's ATen update ops (every
+    energy steps through its own gradient: the library's kernels for recognised energies, autograd otherwise)."""
+
+    def _sample_unfused(self, x, dim, n_steps, n_samples, thin, return_trajectory, return_diagnostics, reset_schedulers,
+                        model_kwargs, generator):
         self._require_cuda_fp32()
         if reset_schedulers:
             self.reset_schedulers()
@@ -410,13 +477,7 @@ class _DescentSampler(BaseSampler):
         n_kept = n_steps // thin
         traj = torch.empty((n, n_kept, *data_shape), dtype=self.dtype, device=self.device) if return_trajectory else None
         diag = {"energy": torch.empty(n_kept, dtype=self.dtype, device=self.device)} if return_diagnostics else None
-        desc = self._descriptor(x, model_kwargs)
-        mu = self._momentum
-        if desc is not None and desc.kind in ("double_well", "harmonic", "rastrigin") and n_steps > 0 and not return_diagnostics:
-            vals, _ = self._advance_schedules(("step_size",), n_steps)
-            out = ops.descent_burst(desc, x.contiguous(), n_steps, vals["step_size"], momentum=mu, traj=traj, thin=thin)
-            return traj if return_trajectory else out
-        # step by step (diagnostics need the energy of every kept state; other energies have no fused descent kernel)
+        mu = self._descent_momentum()
         v = torch.zeros_like(x) if mu is not None else None
         keep = 0
         for i in range(n_steps):
@@ -438,7 +499,7 @@ class _DescentSampler(BaseSampler):
         return (out, diag) if return_diagnostics else out
 
 
-class GradientDescentSampler(_DescentSampler):
+class GradientDescentSampler(FusedDescentMixin, _DescentBase):
     """samplers/gradient_descent.py:16-140: x <- x - eta * grad E(x)."""
 
     def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3, dtype: torch.dtype = torch.float32,
@@ -447,7 +508,7 @@ class GradientDescentSampler(_DescentSampler):
         self._register_param("step_size", step_size, positive=True)
 
 
-class NesterovSampler(_DescentSampler):
+class NesterovSampler(FusedDescentMixin, _DescentBase):
     """samplers/gradient_descent.py:143-276: v <- mu v - eta grad E(x + mu v); x <- x + v."""
 
     def __init__(self, model, step_size: Union[float, BaseScheduler] = 1e-3, momentum: float = 0.9,
@@ -456,5 +517,4 @@ class NesterovSampler(_DescentSampler):
         if not (0 <= momentum < 1):
             raise ValueError("momentum must be in [0, 1)")
         self.momentum = momentum
-        self._momentum = float(momentum)
         self._register_param("step_size", step_size, positive=True)
