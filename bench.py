@@ -65,14 +65,14 @@ UNIT = "chain-steps/s"
 
 
 def c5_gather_mode(world: int) -> str:
-    """C5 gather policy (measured on this pool).  "dma": peer-to-peer copy-engine pushes, no SM used,
+    """C5 gather policy (measured on this pool).  "fused" (default): the wide MLP burst kernel stores
+    the final state of every finished tile into all ranks' gathered tensors itself (NVLink peer stores under the remaining
+    tiles' compute), then a device-side barrier.  The others stay selectable: "dma": peer-to-peer copy-engine pushes, no SM used,
     ~240 GB/s per GPU -- they hide under the 3.2 ms burst while (world - 1) * 205 MB fits (world <= 4: 95 % weak-scaling
     efficiency at 2 GPUs).  "sm": the burst leaves 16 SMs to a peer-store kernel (ebm_peer_push_f32) -- 4.27 ms per step
     at 8 GPUs (1.44 GB out and in per GPU per burst), against 4.67 ms for "nccl" (all-gather on 32 spare SMs) and 6.14 ms
     for DMA pushes."""
-    if C5_GATHER is not None:
-        return C5_GATHER
-    return "dma" if world <= 4 else "sm"
+    return C5_GATHER if C5_GATHER is not None else "fused"
 
 
 def measured_peaks():
@@ -312,11 +312,12 @@ def make_workload(name: str, n_local: int, dev, rng: str = "torch"):
             # the burst-end gather of burst i runs next to burst i+1: leave it SMs (1 for the barrier kernel of the DMA
             # gather; NCCL's channels need more)
             gmode = c5_gather_mode(int(os.environ.get("WORLD_SIZE", "1")))
-            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else {"dma": 1, "sm": 16, "nccl": 32}[gmode]
+            model.sm_margin = SM_MARGIN if SM_MARGIN is not None else {"fused": 0, "dma": 1, "sm": 16, "nccl": 32}[gmode]
         cd = te.ContrastiveDivergence(model, sampler, k_steps=k, persistent=True, buffer_size=n_local, init_steps=0,
                                       new_sample_ratio=0.0, device=dev)
         gen = torch.Generator(dev).manual_seed(1234)
         desc = te.energy_descriptor(model, d, dev)
+        hook = {"peer": None}   # measure() puts the PeerGatherBuffer here for the fused burst-end gather
 
         def step(x, out, it, kev=None):
             # the sampling half of ContrastiveDivergence.forward (losses/contrastive_divergence.py:127-139): start points
@@ -324,10 +325,11 @@ def make_workload(name: str, n_local: int, dev, rng: str = "torch"):
             # batch: the burst kernel reads its start rows from the buffer and writes the final state back into it).
             # The loss/backward is the training objective, not the sampling path.
             if kev: kev[0].record()
-            neg = cd.sample_negatives(x, generator=gen)
+            neg = cd.sample_negatives(x, generator=gen, gather_into=hook["peer"])   # (ends with the cross-rank barrier)
             if kev: kev[1].record()
             return 2, neg  # mlp_wide_prep_kernel, langevin_mlp_wide_kernel (+ torch's randint for the index draw)
 
+        step.hook = hook
         return step, desc, model, 8 * d, k
     raise KeyError(name)
 
@@ -362,7 +364,7 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
     # C2 at N > 1: the burst kernel stores its shard straight into every rank's gathered tensor (symmetric memory, NVLink
     # peer stores) and a device-side barrier replaces the NCCL all-gather; NCCL stays the fallback if peer mapping fails
     peer = None
-    want_peer = workload == "c2" or (workload == "c5" and c5_gather_mode(world) in ("dma", "sm"))
+    want_peer = workload == "c2" or (workload == "c5" and c5_gather_mode(world) in ("fused", "dma", "sm"))
     if world > 1 and want_peer and not nccl_gather:
         ok = torch.ones(1, device=dev)
         try:
@@ -392,8 +394,11 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
 
     # C5 (weak scaling, 1.6 GB gathered per GPU at N = 8): the gather of burst i runs on a side stream underneath
     # burst i+1 (the negatives are a fresh tensor per burst; the loss needs only the local ones, core/base_loss.py:131-134)
-    side = torch.cuda.Stream(device=dev) if (world > 1 and workload in WEAK) else None
-    fused_gather = peer is not None and workload == "c2"   # the burst kernel itself stores into the peers
+    c5_fused = peer is not None and workload == "c5" and c5_gather_mode(world) == "fused"
+    if c5_fused:
+        step.hook["peer"] = peer
+    side = torch.cuda.Stream(device=dev) if (world > 1 and workload in WEAK and not c5_fused) else None
+    fused_gather = peer is not None and (workload == "c2" or c5_fused)   # the burst kernel itself stores into the peers
 
     def gather(res):
         if side is None:
@@ -679,7 +684,7 @@ def _reference_langevin(ref, workload: str, device):
     if workload == "c1":
         model = GaussianModel(mean=torch.zeros(2), cov=torch.tensor([[1.0, 0.8], [0.8, 1.0]])).to(device)
     elif workload == "c2":
-        model = DoubleWellModel(barrier_height=2.0, b=1.0)
+        model = DoubleWellModel(barrier_height=2.0, b=1.0).to(device)   # (BaseModel.gradient moves x to the MODEL's device)
     else:
         model = _RefMLP(784 if workload in ("c3", "c5") else 128).to(device)
     return LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=device)
@@ -780,7 +785,7 @@ def torch_cuda_hmc_baseline(dev, workload: str, ref=None):
         from torchebm.core import RastriginModel
         from torchebm.samplers import HamiltonianMonteCarlo
 
-        model = RastriginModel(a=10.0) if workload == "c4" else _RefMLP(128).to(dev)
+        model = (RastriginModel(a=10.0) if workload == "c4" else _RefMLP(128)).to(dev)
         smp = HamiltonianMonteCarlo(model, step_size=h, n_leapfrog_steps=L, device=dev)
         run = lambda: smp.sample(x=x0, n_steps=2, generator=gen)
         kind, what = "reference", "unmodified torchebm.samplers.HamiltonianMonteCarlo from baseline/_ref"
@@ -884,7 +889,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference baselines (CPU, same-GPU, Triton)")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: use the NCCL all-gather instead of fused peer stores")
     ap.add_argument("--sm-margin", type=int, default=None, help="c5, N > 1: SMs the persistent burst leaves to the gather")
-    ap.add_argument("--c5-gather", default=None, choices=["dma", "sm", "nccl"],
+    ap.add_argument("--c5-gather", default=None, choices=["fused", "dma", "sm", "nccl"],
                     help="c5, N > 1: peer DMA copies, SM-driven peer-store kernel on the spare SMs, or NCCL (default by world size)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

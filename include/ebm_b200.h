@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 6
+#define EBM_ABI_VERSION 7
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -147,9 +147,10 @@ int ebm_descent_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_ou
  * collective of the sharded path) fused into the kernel's final store: besides x_out[n, dim] the final state is written
  * at rows [row_offset, row_offset + n) of EVERY rank's gathered buffer.  peer_out_host[w] (host array of `world` device
  * pointers, world <= 16) is rank w's gathered [n_total, dim] buffer as mapped into THIS process (peer / symmetric
- * memory; the own rank's entry is its local buffer).  Remote stores travel over NVLink from inside the burst kernel
- * (elementwise energies) or as copy-engine pushes (other energies).  The caller runs a cross-rank barrier on the stream
- * afterwards, before any rank reads its gathered buffer. */
+ * memory; the own rank's entry is its local buffer).  Remote stores travel over NVLink from inside the burst kernel's
+ * final state store (elementwise energies; MLP energies on the tensor-core kernels, i.e. ebm_pcd_langevin_fused(e) != 0)
+ * or as copy-engine pushes (other energies).  The caller runs a cross-rank barrier on the stream afterwards, before any
+ * rank reads its gathered buffer.  Replaces the all_gather of the negatives (utils/distributed.py:43-70). */
 int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
                                   const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
                                   const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
@@ -219,6 +220,16 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
                                const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
                                const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
                                int64_t* new_ptr_host, void* stream);
+/* The same call on one rank of a chain-sharded box (BASELINE config 5): the negatives also land at rows
+ * [row_offset, row_offset + n) of every rank's gathered buffer, from inside the burst kernel's final store where it has
+ * a peer-store epilogue.  peer_out_host / world / row_offset and the barrier rule as in ebm_langevin_burst_gather_f32. */
+int ebm_pcd_langevin_burst_gather_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
+                                      int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
+                                      const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                      const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                      const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
+                                      int64_t* new_ptr_host, float* const* peer_out_host, int32_t world,
+                                      int64_t row_offset, void* stream);
 
 /* Bursts that also produce the reference's per-kept-sample diagnostics (return_diagnostics=True:
  * samplers/langevin_dynamics.py:170-185, samplers/hmc.py:294-310) in the same call:

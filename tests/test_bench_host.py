@@ -46,6 +46,6 @@ def test_measured_peaks_fallback_and_partial_file(tmp_path, monkeypatch):
 
 def test_c5_gather_policy():
     b = _bench()
-    assert [b.c5_gather_mode(w) for w in (2, 4, 8)] == ["dma", "dma", "sm"]
+    assert [b.c5_gather_mode(w) for w in (2, 4, 8)] == ["fused"] * 3   # peer stores from inside the burst kernel
     b.C5_GATHER = "nccl"
     assert b.c5_gather_mode(2) == "nccl"

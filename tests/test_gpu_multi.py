@@ -80,6 +80,37 @@ def _worker(rank, world, port, n_total, d, k, result_dir):
         buf.push_sm(odd, 8)
         torch.cuda.synchronize()
         results["mlp_push_sm"] = bool(torch.equal(buf.tensor, gather_chains(odd)))
+        # MLP bursts: the tensor-core kernels store the final state of every finished tile into all gathered tensors
+        # (narrow kernel at dim 96, wide kernel at dim 200), plain burst and the one-call persistent-CD form
+        for dm in (d, 200):
+            torch.manual_seed(5)
+            mlp = te.MLPEnergy(dim=dm, hidden=64, activation="silu").to(dev)
+            desc = te.energy_descriptor(mlp, dm, dev)
+            xl = torch.randn(hi - lo, dm, generator=torch.Generator().manual_seed(10 + rank)).to(dev)
+            buf = PeerGatherBuffer(n_total, dm, dev)
+            buf.tensor.fill_(float("nan"))
+            buf.barrier()
+            local = buf.burst(desc, xl, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=0)
+            torch.cuda.synchronize()
+            want_local = ops.langevin_burst(desc, xl, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=0)
+            results[f"mlp_fused_{dm}"] = bool(torch.equal(local, want_local) and torch.equal(buf.tensor, gather_chains(want_local)))
+            buf.barrier()
+            sampler = te.LangevinDynamics(mlp, step_size=0.01, noise_scale=1.0, device=dev).with_rng("native")
+            cds = [te.ContrastiveDivergence(mlp, sampler, k_steps=k, persistent=True, buffer_size=hi - lo, init_steps=0,
+                                            new_sample_ratio=ratio, device=dev) for ratio in (0.0, 0.0, 0.05, 0.05)]
+            for j, cd in enumerate(cds):   # pairs: (with gather, without) must agree in negatives and buffer
+                gen = torch.Generator(dev).manual_seed(31 + rank)
+                buf.tensor.fill_(float("nan"))
+                buf.barrier()
+                neg = cd.sample_negatives(xl, generator=gen, gather_into=buf if j % 2 == 0 else None)
+                torch.cuda.synchronize()
+                if j % 2 == 0:
+                    kept, kept_buf, gathered = neg.clone(), cd.replay_buffer.clone(), buf.tensor.clone()
+                else:
+                    results[f"pcd_gather_{dm}_{j // 2}"] = bool(
+                        torch.equal(neg, kept) and torch.equal(cd.replay_buffer, kept_buf)
+                        and torch.equal(gathered, gather_chains(neg)))
+                buf.barrier()
         torch.save(results, os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()

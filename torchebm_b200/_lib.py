@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # EBM_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); still no fallback of any kind
 LIB_PATH = os.environ.get("EBM_B200_LIB") or os.path.join(HERE, "lib", "libebm_b200.so")
 
-EBM_ABI_VERSION = 6
+EBM_ABI_VERSION = 7
 
 ENERGY_DOUBLE_WELL, ENERGY_HARMONIC, ENERGY_RASTRIGIN, ENERGY_GAUSSIAN, ENERGY_MOG, ENERGY_MLP = range(6)
 ACT_SILU, ACT_TANH, ACT_RELU, ACT_SOFTPLUS = range(4)
@@ -81,6 +81,9 @@ PROTOTYPES = {
     "ebm_pcd_langevin_fused": (C.c_int, [_DESC]),
     "ebm_pcd_langevin_burst_f32": (C.c_int, [_DESC, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _PD, _PD, _I32, _PF, _I32, _U64, _U64,
                                              _P, _P, _I64, _P, C.POINTER(C.c_int64), _P]),
+    "ebm_pcd_langevin_burst_gather_f32": (C.c_int, [_DESC, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _PD, _PD, _I32, _PF, _I32, _U64,
+                                                    _U64, _P, _P, _I64, _P, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), _I32,
+                                                    _I64, _P]),
     "ebm_langevin_burst_diag_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _PD, _PD, _I32, _PF, _I32, _U64, _U64, _P, _P, _I32, _I32,
                                               _P, _P, _P, _P, _P, _P]),
     "ebm_hmc_burst_diag_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _I32, _PD, _I32, _I32, _F64, _P, _I32, _U64, _U64, _P, _P, _P,

@@ -572,6 +572,23 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
   return langevin_dispatch(c);
 }
 
+}  // extern "C"
+
+// burst kernels with a peer-store epilogue: the elementwise kernel and the two tensor-core MLP kernels
+static bool burst_stores_to_peers(const EbmEnergyDesc* e) {
+  return e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN ||
+         (e->kind == EBM_ENERGY_MLP && (e->precision == EBM_MLP_BF16X3 || e->precision == EBM_MLP_BF16));
+}
+
+// every other burst kernel: copy-engine pushes of the finished shard into every gathered buffer
+static int push_to_peers(const float* src, size_t numel, float* const* peers, int world, long long elem_off, cudaStream_t st) {
+  for (int w = 0; w < world; ++w)
+    EBM_CUDA(cudaMemcpyAsync(peers[w] + elem_off, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" {
+
 int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
                                   const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
                                   const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
@@ -587,17 +604,13 @@ int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, flo
   EBM_CHECK_ARG(peer_out_host && world >= 1 && world <= kMaxPeers, "peer_out_host must hold 1..16 pointers");
   EBM_CHECK_ARG(row_offset >= 0, "row_offset must be non-negative");
   for (int w = 0; w < world; ++w) EBM_CHECK_ARG(peer_out_host[w], "null peer pointer");
-  const bool fused = e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN;
+  const bool fused = burst_stores_to_peers(e);
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, nullptr, 0, 0,
                  fused ? peer_out_host : nullptr, fused ? world : 0, row_offset, 0};
   rc = langevin_dispatch(c);
   if (rc || fused) return rc;
-  // energies whose burst kernel has no peer-store epilogue yet: copy-engine pushes of the shard into every buffer
-  const size_t bytes = (size_t)n * e->dim * sizeof(float);
-  for (int w = 0; w < world; ++w)
-    EBM_CUDA(cudaMemcpyAsync(peer_out_host[w] + row_offset * e->dim, x_out, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return 0;
+  return push_to_peers(x_out, (size_t)n * e->dim, peer_out_host, world, row_offset * e->dim, (cudaStream_t)stream);
 }
 
 int ebm_langevin_heun_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
@@ -648,14 +661,26 @@ int ebm_pcd_langevin_fused(const EbmEnergyDesc* e) {
   return e && e->kind == EBM_ENERGY_MLP && (e->precision == EBM_MLP_BF16X3 || e->precision == EBM_MLP_BF16) ? 1 : 0;
 }
 
-int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
-                               int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
-                               const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
-                               const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
-                               const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
-                               int64_t* new_ptr_host, void* stream) {
+}  // extern "C"
+
+// the persistent-CD burst; peers != NULL: the negatives also land in every rank's gathered buffer (from inside the
+// burst kernel's final store when it has a peer-store epilogue, copy-engine pushes otherwise)
+static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
+                                   int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
+                                   const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                   const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                   const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
+                                   int64_t* new_ptr_host, float* const* peers, int32_t world, int64_t row_offset,
+                                   void* stream) {
   int rc = validate_desc(e);
   if (rc) return rc;
+  if (peers) {
+    EBM_CHECK_ARG(world >= 1 && world <= kMaxPeers, "peer_out_host must hold 1..16 pointers");
+    EBM_CHECK_ARG(row_offset >= 0, "row_offset must be non-negative");
+    for (int w = 0; w < world; ++w) EBM_CHECK_ARG(peers[w], "null peer pointer");
+  } else {
+    world = 0;
+  }
   EBM_CHECK_ARG(buffer && x_out && buffer_rows > 0 && n > 0, "buffer/x_out must be non-null, sizes positive");
   EBM_CHECK_ARG(idx || n <= buffer_rows, "idx == NULL (chain i starts from row i) needs n <= buffer_rows");
   EBM_CHECK_ARG(ptr >= 0 && ptr < buffer_rows, "ptr out of range");
@@ -682,8 +707,8 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
       if (rc) return rc;
     }
     LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
-                   rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, buffer, 0, 0, nullptr, 0, 0, 0,
-                   nullptr};
+                   rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, buffer, 0, 0, peers, world,
+                   row_offset, 0, nullptr};
     rc = langevin_dispatch(c);
     if (rc) return rc;
     if (new_ptr_host) *new_ptr_host = 0;
@@ -692,7 +717,7 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
     // row may be another chain's source row)
     LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                    rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, (const long long*)idx, nullptr, 0, 0,
-                   nullptr, 0, 0, 0, nullptr};
+                   peers, world, row_offset, 0, nullptr};
     rc = langevin_dispatch(c);
     if (rc) return rc;
     rc = ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
@@ -716,9 +741,39 @@ int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t bu
     if (rc) return rc;
     rc = ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
     if (rc) return rc;
+    if (world > 0) {
+      rc = push_to_peers(x_out, (size_t)n * row_elems, peers, world, row_offset * row_elems, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
   }
   if (energy_out) return ebm_energy_f32(e, x_out, n, energy_out, stream);   // E(x-) of the negatives
   return 0;
+}
+
+extern "C" {
+
+int ebm_pcd_langevin_burst_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
+                               int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
+                               const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                               const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                               const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
+                               int64_t* new_ptr_host, void* stream) {
+  return pcd_langevin_burst_impl(e, buffer, buffer_rows, idx, ptr, x_out, scratch, n, n_steps, step_size_host,
+                                 noise_scale_host, schedule_len, clamp_lo_hi_host, rng_mode, seed, offset, noise_rows, noise,
+                                 n_noise, energy_out, new_ptr_host, nullptr, 0, 0, stream);
+}
+
+int ebm_pcd_langevin_burst_gather_f32(const EbmEnergyDesc* e, float* buffer, int64_t buffer_rows, const int64_t* idx,
+                                      int64_t ptr, float* x_out, float* scratch, int64_t n, int32_t n_steps,
+                                      const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
+                                      const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,
+                                      const int64_t* noise_rows, const float* noise, int64_t n_noise, float* energy_out,
+                                      int64_t* new_ptr_host, float* const* peer_out_host, int32_t world,
+                                      int64_t row_offset, void* stream) {
+  EBM_CHECK_ARG(peer_out_host, "peer_out_host must be non-null");
+  return pcd_langevin_burst_impl(e, buffer, buffer_rows, idx, ptr, x_out, scratch, n, n_steps, step_size_host,
+                                 noise_scale_host, schedule_len, clamp_lo_hi_host, rng_mode, seed, offset, noise_rows, noise,
+                                 n_noise, energy_out, new_ptr_host, peer_out_host, world, row_offset, stream);
 }
 
 int ebm_langevin_burst_host_f32(const EbmEnergyDesc* e, const float* x_in_host, float* x_out_host, float* scratch_dev,

@@ -67,6 +67,10 @@ struct TcParams {
   RowRng rng;
   PhiloxKeys keys;    // round keys of (rng.k0, rng.k1)
   MlpSchedule sched;  // balanced (tile, step-range) split, mlp_schedule.cuh
+  // burst-end gather fused into the final state store (last launch of a burst only), see ebm_mlp_wide.cu
+  int n_peers;
+  long long peer_off;
+  float* peers[kMaxPeers];
 };
 
 struct TcSmemLayout {
@@ -625,6 +629,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
         for (int j = 0; j < kTcCols / 2; ++j) unpack2(X[j], xs[2 * j], xs[2 * j + 1]);
         tc_store_row32(P.x_out, grow, P.d, col_base, rv, xs);
         if (P.x_out2 && s1 == P.n_steps) tc_store_row32(P.x_out2, grow, P.d, col_base, rv, xs);
+        if (s1 == P.n_steps)
+          for (int w = 0; w < P.n_peers; ++w) tc_store_row32(P.peers[w] + P.peer_off, grow, P.d, col_base, rv, xs);
       }
       if (s1 < P.n_steps) mlp_unit_release(P.sched);  // the rest of this tile's burst runs on the next CTA
     }
@@ -1030,6 +1036,12 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.x_out = c.x_out;
     P.row_index = (done == 0) ? c.row_index : nullptr;
     P.x_out2 = (done + chunk == c.n_steps) ? c.x_out2 : nullptr;
+    P.n_peers = 0;
+    if (c.n_peers > 0 && done + chunk == c.n_steps) {
+      P.n_peers = c.n_peers;
+      P.peer_off = c.peer_row_offset * e->dim;
+      for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
+    }
     P.n_steps = chunk;
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;

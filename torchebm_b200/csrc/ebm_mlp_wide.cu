@@ -85,6 +85,12 @@ struct WdParams {
   float clamp_lo, clamp_hi;
   RowRng rng;
   MlpSchedule sched;
+  // burst-end gather fused into the final state store (last launch of a burst only): the final state of a tile is also
+  // stored at element offset peer_off of every rank's peer-mapped gathered buffer, over NVLink for the remote ones.
+  // Tiles finish one after the other on a CTA, so all but each CTA's last tile drain underneath the remaining compute.
+  int n_peers;
+  long long peer_off;
+  float* peers[kMaxPeers];
 };
 
 __device__ __forceinline__ uint32_t wd_bar(uint8_t* smem, int idx) { return smem_u32(smem + WdSmem::bars + idx * 8); }
@@ -454,6 +460,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     // widest aligned access every pointer of this launch allows
     const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj | (uintptr_t)P.x_out2;
     const int vec = (P.d % 8 == 0 && (ptr_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (ptr_bits & 15) == 0) ? 1 : 0);
+    uintptr_t peer_bits = 0;
+    for (int w = 0; w < P.n_peers; ++w) peer_bits |= (uintptr_t)(P.peers[w] + P.peer_off);
+    const int vec_peer = (P.d % 8 == 0 && (peer_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (peer_bits & 15) == 0) ? 1 : 0);
     uint32_t acc_par = 0, g_par = 0;  // g_par: bit b = parity of g_full[b]
 
     for (int tile = units->t_last; tile >= units->t_first; --tile) {
@@ -486,7 +495,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const float h = tab.h[ti], c1 = tab.c1[ti], c2 = tab.c2[ti];
         const float* xsrc = (k == 0) ? P.x_in : P.x_out;
         const long long xrow = (k == 0 && P.row_index && rv) ? P.row_index[grow] : grow;
-        const bool final_step = P.x_out2 && (k == K - 1);
+        const bool final_x2 = P.x_out2 && (k == K - 1);
+        const bool final_peers = P.n_peers > 0 && (k == K - 1);
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM [256, 384)
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
         tcgen05_fence_after();
@@ -604,7 +614,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           wd_publish(xa_full + 8 * xb);
           if (active) {
             wd_store_x16(P.x_out, grow * P.d, col0, P.d, rv, vec, xc);
-            if (final_step) wd_store_x16(P.x_out2, grow * P.d, col0, P.d, rv, vec, xc);
+            if (final_x2) wd_store_x16(P.x_out2, grow * P.d, col0, P.d, rv, vec, xc);
+            if (final_peers) {
+              for (int w = 0; w < P.n_peers; ++w) wd_store_x16(P.peers[w] + P.peer_off, grow * P.d, col0, P.d, rv, vec_peer, xc);
+            }
             if (keep_now) wd_store_x16(P.traj, (grow * P.n_kept + (kept - 1)) * P.d, col0, P.d, rv, vec, xc);
           }
         }
@@ -894,6 +907,12 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     P.x_out = c.x_out;
     P.row_index = (done == 0) ? c.row_index : nullptr;
     P.x_out2 = (done + chunk == c.n_steps) ? c.x_out2 : nullptr;
+    P.n_peers = 0;
+    if (c.n_peers > 0 && done + chunk == c.n_steps) {
+      P.n_peers = c.n_peers;
+      P.peer_off = c.peer_row_offset * e->dim;
+      for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
+    }
     P.n_steps = chunk;
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;

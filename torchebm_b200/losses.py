@@ -66,13 +66,27 @@ class FusedPCDMixin:
         return noise_rows, noise
 
     def sample_negatives(self, x: torch.Tensor, model_kwargs: Optional[dict] = None,
-                         generator: Optional[torch.Generator] = None, energy_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         generator: Optional[torch.Generator] = None, energy_out: Optional[torch.Tensor] = None,
+                         gather_into=None) -> torch.Tensor:
         """The sampling half of `ContrastiveDivergence.forward` (contrastive_divergence.py:127-139): start points,
         `k_steps` of the sampler, buffer write-back.  Same draws from `generator`, same buffer and pointer state as
         `get_start_points` -> `sampler.sample` -> `update_buffer`; when the sampler offers `sample_from_buffer` and
         nothing stands in the way (2-D state, no conditioning) the three steps are ONE library call: exploration noise
         included, and with `buffer_size == batch` the burst kernel reads its start rows straight from the replay buffer
-        and writes its final state straight back.  `energy_out[batch]` (optional) receives E(x-)."""
+        and writes its final state straight back.  `energy_out[batch]` (optional) receives E(x-).  `gather_into` (a
+        `distributed.PeerGatherBuffer`, chain-sharded runs): the negatives also land in every rank's gathered tensor --
+        the all-gather of utils/distributed.py:43-70 -- stored by the burst kernel itself when the one-call path runs,
+        pushed afterwards otherwise; complete on all ranks after the barrier this method issues."""
+        pred = self._sample_negatives(x, model_kwargs, generator, energy_out, gather_into)
+        if gather_into is not None:
+            if not getattr(self, "_gathered_in_burst", False):
+                gather_into.push(pred)       # (push ends with the barrier)
+            else:
+                gather_into.barrier()
+        return pred
+
+    def _sample_negatives(self, x, model_kwargs, generator, energy_out, gather_into) -> torch.Tensor:
+        self._gathered_in_burst = False
         fused = getattr(self.sampler, "sample_from_buffer", None)
         if self.persistent and fused is not None and not model_kwargs and x.ndim == 2:
             x = x.to(device=self.device, dtype=self.dtype)
@@ -87,9 +101,11 @@ class FusedPCDMixin:
                 # buffer_size == batch: the stratified draw has stride 1, i.e. it is arange(batch) by construction
                 # (base_loss.py:307-312); the library takes its no-gather form only when told so explicitly (idx None)
                 identity = self.buffer_size == batch
+                extra = {} if gather_into is None else {"gather_into": gather_into}
                 res = fused(self.replay_buffer, None if identity else indices, self._buffer_ptr_int, self.k_steps,
-                            noise_rows=noise_rows, noise=noise, energy_out=energy_out, generator=generator)
+                            noise_rows=noise_rows, noise=noise, energy_out=energy_out, generator=generator, **extra)
                 if res is not None:
+                    self._gathered_in_burst = gather_into is not None
                     pred, new_ptr = res
                     self._buffer_ptr_int = new_ptr
                     self.buffer_ptr.fill_(new_ptr)

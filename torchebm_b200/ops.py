@@ -278,11 +278,13 @@ def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Option
                        step_sizes: Sequence[float], noise_scales: Sequence[float], *,
                        clamp: Optional[Tuple[float, float]] = None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0,
                        offset: int = 0, noise_rows: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
-                       energy_out: Optional[torch.Tensor] = None, batch: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+                       energy_out: Optional[torch.Tensor] = None, batch: Optional[int] = None,
+                       peer_ptrs: Optional[Sequence[int]] = None, row_offset: int = 0) -> Tuple[torch.Tensor, int]:
     """Start points `buffer[idx]` (+ 0.01 * noise[j] on chain noise_rows[j]) -> K-step burst -> FIFO write-back into
     `buffer` (in place).  `idx=None`: chain i starts from row i (`batch` chains, default the whole buffer) -- the
     stride-1 case of core/base_loss.py:307-312.  Returns the negatives and the new FIFO pointer (host int, no sync);
-    `energy_out[n]` receives E(negatives)."""
+    `energy_out[n]` receives E(negatives).  `peer_ptrs` (see `langevin_burst_gather`): the negatives also land at rows
+    `[row_offset, row_offset + n)` of every rank's gathered buffer; a cross-rank barrier must follow on the stream."""
     if not buffer.is_contiguous() or buffer.ndim != 2:
         raise ValueError("replay buffer must be a contiguous [S, D] tensor")
     buffer = _req(buffer, "buffer")
@@ -307,12 +309,17 @@ def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Option
     hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
     cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
     new_ptr = C.c_int64(0)
-    with torch.cuda.device(buffer.device):
-        rc = _lib.load().ebm_pcd_langevin_burst_f32(
-            C.byref(desc.c), buffer.data_ptr(), buffer.shape[0], _ptr(idx), int(ptr), out.data_ptr(), _ptr(scratch), n,
+    args = (C.byref(desc.c), buffer.data_ptr(), buffer.shape[0], _ptr(idx), int(ptr), out.data_ptr(), _ptr(scratch), n,
             int(n_steps), hs, ns, len(step_sizes), cl, int(rng_mode), int(seed), int(offset), _ptr(noise_rows), _ptr(noise),
-            n_noise, _ptr(energy_out), C.byref(new_ptr), _stream(buffer.device))
-    _lib.check(rc, "ebm_pcd_langevin_burst_f32")
+            n_noise, _ptr(energy_out), C.byref(new_ptr))
+    with torch.cuda.device(buffer.device):
+        if peer_ptrs is None:
+            rc = _lib.load().ebm_pcd_langevin_burst_f32(*args, _stream(buffer.device))
+        else:
+            peers = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            rc = _lib.load().ebm_pcd_langevin_burst_gather_f32(*args, peers, len(peer_ptrs), int(row_offset),
+                                                               _stream(buffer.device))
+    _lib.check(rc, "ebm_pcd_langevin_burst_f32" if peer_ptrs is None else "ebm_pcd_langevin_burst_gather_f32")
     return out, int(new_ptr.value)
 
 

@@ -143,14 +143,16 @@ class FusedLangevinMixin(_RngAttribute):
     def sample_from_buffer(self, buffer: torch.Tensor, indices: Optional[torch.Tensor], ptr: int, n_steps: int, *,
                            noise_rows: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                            energy_out: Optional[torch.Tensor] = None, reset_schedulers: bool = True,
-                           generator: Optional[torch.Generator] = None):
+                           generator: Optional[torch.Generator] = None, gather_into=None):
         """Persistent-CD negatives in one library call: start points `buffer[indices]` (`indices=None`: row i for chain
         i, the stride-1 case where the whole buffer is replaced) plus `0.01 * noise[j]` on row `noise_rows[j]`, `n_steps`
         Langevin steps, FIFO write-back into `buffer` at `ptr` (get_start_points + sample + update_buffer of
         core/base_loss.py:266-337,390-426 and losses/contrastive_divergence.py:127-139); `energy_out[n]` receives
         E(x-) of the returned negatives.  Same scheduler and generator semantics as
         `sample(x=start_points, n_steps=n_steps, generator=generator)`.  Returns `(negatives, new_ptr)`, or None when
-        this sampler / energy has no library kernel for it (the caller then takes the three-call path)."""
+        this sampler / energy has no library kernel for it (the caller then takes the three-call path).
+        `gather_into` (a `distributed.PeerGatherBuffer`): the negatives of this rank also land in every rank's gathered
+        tensor, stored by the burst kernel itself; the caller issues `gather_into.barrier()` before reading it."""
         if sde_scheme_of(self.integrator) != "euler_maruyama" or buffer.ndim != 2 or not buffer.is_cuda:
             return None   # (the one-call PCD path is Euler-Maruyama only)
         if self.device.type != "cuda" or self.dtype != torch.float32:
@@ -166,7 +168,10 @@ class FusedLangevinMixin(_RngAttribute):
         vals, _ = advance_schedules(self, ("step_size", "noise_scale"), n_steps)
         out, new_ptr = ops.pcd_langevin_burst(desc, buffer, indices, ptr, n_steps, vals["step_size"], vals["noise_scale"],
                                               clamp=self.clamp, rng_mode=rng_mode, seed=seed, offset=offset,
-                                              noise_rows=noise_rows, noise=noise, energy_out=energy_out)
+                                              noise_rows=noise_rows, noise=noise, energy_out=energy_out,
+                                              **({} if gather_into is None else
+                                                 {"peer_ptrs": gather_into.ptrs,
+                                                  "row_offset": gather_into.rank * gather_into.rows_per_rank}))
         gen.set_offset(offset + ops.rng_consumed_langevin(self.device, out.numel(), n_steps, rng_mode))
         return out, new_ptr
 
