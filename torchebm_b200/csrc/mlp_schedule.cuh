@@ -15,7 +15,7 @@
 
 namespace ebm {
 
-constexpr int kMlpFlagBytes = 1024;  // one int per CTA (grid <= number of SMs <= 256)
+constexpr int kMlpFlagBytes = 2048;  // one int per worker (a CTA, or one of the two tile pipelines of a CTA; <= 512)
 
 struct MlpSchedule {
   long long quota;  // work quanta per CTA (floor)
@@ -29,8 +29,10 @@ struct MlpSchedule {
 struct MlpUnits {
   int t_first, t_last, first_s0, last_s1;
 };
-__device__ __forceinline__ void mlp_units_compute(const MlpSchedule& s, int K, volatile MlpUnits* u) {
-  const long long b = blockIdx.x;
+// `worker` = index of the entity that walks a range: the CTA, or (kernels that run two tile pipelines per CTA)
+// 2 * blockIdx.x + pipeline; the host sets the schedule up for as many workers
+__device__ __forceinline__ void mlp_units_compute(const MlpSchedule& s, int K, volatile MlpUnits* u, long long worker) {
+  const long long b = worker;
   const long long lin_begin = (b * s.quota + (b < s.rem ? b : s.rem)) * s.gran;
   const long long lin_end = lin_begin + (s.quota + (b < s.rem ? 1 : 0)) * s.gran;
   const long long tf = lin_begin / K, tl = (lin_end - 1) / K;
@@ -39,20 +41,24 @@ __device__ __forceinline__ void mlp_units_compute(const MlpSchedule& s, int K, v
   u->first_s0 = (int)(lin_begin - tf * K);
   u->last_s1 = (int)(lin_end - tl * K);
 }
+__device__ __forceinline__ void mlp_units_compute(const MlpSchedule& s, int K, volatile MlpUnits* u) {
+  mlp_units_compute(s, K, u, blockIdx.x);
+}
 // steps [s0, s1) of `tile` that belong to this CTA
 __device__ __forceinline__ int mlp_unit_s0(const volatile MlpUnits* u, int tile) { return tile == u->t_first ? u->first_s0 : 0; }
 __device__ __forceinline__ int mlp_unit_s1(const volatile MlpUnits* u, int tile, int K) { return tile == u->t_last ? u->last_s1 : K; }
 
 // called by every epilogue warp (all lanes) after its last global store of a head unit
-__device__ __forceinline__ void mlp_unit_release(const MlpSchedule& s) {
+__device__ __forceinline__ void mlp_unit_release(const MlpSchedule& s, int worker) {
   __threadfence();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) atomicAdd(s.flags + blockIdx.x, 1);
+  if ((threadIdx.x & 31) == 0) atomicAdd(s.flags + worker, 1);
 }
+__device__ __forceinline__ void mlp_unit_release(const MlpSchedule& s) { mlp_unit_release(s, blockIdx.x); }
 // called by every epilogue warp (all lanes) before its first global load of a tail unit
-__device__ __forceinline__ void mlp_unit_acquire(const MlpSchedule& s, int n_warps) {
+__device__ __forceinline__ void mlp_unit_acquire(const MlpSchedule& s, int n_warps, int worker) {
   if ((threadIdx.x & 31) == 0) {
-    const int* f = s.flags + (blockIdx.x - 1);
+    const int* f = s.flags + (worker - 1);
     int v;
     do {
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
@@ -62,17 +68,18 @@ __device__ __forceinline__ void mlp_unit_acquire(const MlpSchedule& s, int n_war
   __syncwarp();
 }
 
-// host: fill the schedule for `tiles` x `k_steps` on `grid` CTAs and zero the flags on the stream
+__device__ __forceinline__ void mlp_unit_acquire(const MlpSchedule& s, int n_warps) { mlp_unit_acquire(s, n_warps, blockIdx.x); }
+
+// host: fill the schedule for `tiles` x `k_steps` on `grid` workers and zero the flags on the stream
 inline int mlp_schedule_setup(MlpSchedule& s, long long tiles, int k_steps, int grid, int* flags, cudaStream_t st) {
   const long long total = tiles * (long long)k_steps;
   s.quota = total / grid;
   s.rem = (int)(total % grid);
   s.gran = 1;
   s.flags = flags;
-  if (tiles > grid) {  // only then can a tile be shared by two CTAs
-    cudaError_t err = cudaMemsetAsync(flags, 0, kMlpFlagBytes, st);
-    if (err != cudaSuccess) return (int)err;
-  }
+  // (a tile can be shared by two workers whenever the ranges do not fall on tile boundaries)
+  cudaError_t err = cudaMemsetAsync(flags, 0, kMlpFlagBytes, st);
+  if (err != cudaSuccess) return (int)err;
   return 0;
 }
 
