@@ -47,15 +47,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
 
   if (warp < kTcRoleWarps) {
     if (kTcRoleRegs < 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcRoleRegs));
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {   // converged: all lanes wait, one elected lane issues (umma.cuh: elect_one)
+      const bool leader = elect_one();
       uint32_t parity = 0;
       for (int tile = units->t_last; tile >= units->t_first; --tile) {
         const int n_unit_steps = mlp_unit_s1(units, tile, P.n_steps) - mlp_unit_s0(units, tile);
         for (int k = 0; k < n_unit_steps; ++k) {
-          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity); parity ^= 1;
-          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity); parity ^= 1;
-          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity); parity ^= 1;
-          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity, leader); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity, leader); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity, leader); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity, leader); parity ^= 1;
         }
       }
     }
@@ -331,15 +332,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
   const int L = H.n_leapfrog;
 
   if (warp < kTcRoleWarps) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {   // converged: all lanes wait, one elected lane issues (umma.cuh: elect_one)
+      const bool leader = elect_one();
       uint32_t parity = 0;
       for (int tile = units->t_last; tile >= units->t_first; --tile) {
         const int n_evals = (mlp_unit_s1(units, tile, H.n_prop) - mlp_unit_s0(units, tile)) * (L + 1);
         for (int k = 0; k < n_evals; ++k) {
-          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity); parity ^= 1;
-          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity); parity ^= 1;
-          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity); parity ^= 1;
-          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity, leader); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity, leader); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity, leader); parity ^= 1;
+          tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity, leader); parity ^= 1;
         }
       }
     }

@@ -76,17 +76,6 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-// true in exactly one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // a thread's 64 consecutive columns of one row <-> global memory, as packed pairs
 __device__ __forceinline__ void t2_load_row(const float* __restrict__ src, long long grow, int d, int col_base, bool rv,
                                             f32x2 (&X)[kT2Cols / 2]) {

@@ -252,11 +252,12 @@ __device__ __forceinline__ void wd_store_x16(float* __restrict__ dst, long long 
   }
 }
 
-// ---- MMA issue helpers (one thread) -----------------------------------------------------------------------
+// ---- MMA issue helpers (converged warp, one elected lane issues) -----------------------------------------------------------------------
 // `ksteps` k-steps of 16; descriptors advance by (a_step, b_step) bytes per k-step; three passes for split operands
 __device__ __forceinline__ void wd_mma_block(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b_hi,
                                              uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
-                                             int k_begin, int k_end, int passes, bool accumulate_first) {
+                                             int k_begin, int k_end, int passes, bool accumulate_first, bool leader) {
+  if (!leader) return;   // (the warp runs converged; one elected lane issues, see umma.cuh: elect_one)
   for (int kk = k_begin; kk < k_end; ++kk) {
     const uint64_t ah = make_smem_desc(a_hi + kk * a_step, kWdM * 16, 128);
     const uint64_t bh = make_smem_desc(b_hi + kk * b_step, b_lbo, b_sbo);
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     }
   } else if (warp == 0) {
     // ---- MMA issue ----------------------------------------------------------------------------------------------
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       const uint32_t a_hi = smem_u32(smem + WdSmem::a_hi), a_lo = smem_u32(smem + WdSmem::a_lo);
       const uint32_t xa = smem_u32(smem + WdSmem::xa);
       const uint32_t ring = smem_u32(smem + WdSmem::ring);
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       uint32_t it = 0;                        // ring item counter (consumer side)
       uint32_t xcnt = 0, a_par = 0;         // xcnt: running count of published state chunks (buffer = xcnt & 1)
       auto ring_wait = [&](uint32_t item) { mbar_wait(wd_bar(smem, WdSmem::ring_full + item % kWdStages), (item / kWdStages) & 1); };
-      auto ring_release = [&](uint32_t item) { mma_commit(wd_bar(smem, WdSmem::ring_empty + item % kWdStages)); };
+      auto ring_release = [&](uint32_t item) { if (leader) mma_commit(wd_bar(smem, WdSmem::ring_empty + item % kWdStages)); };
       auto stage_addr = [&](uint32_t item) { return ring + (item % kWdStages) * kWdStageBytes; };
       // forward product of state chunk c: z1 (+)= xa . W1_c^T
       auto gemm1_chunk = [&](uint32_t item, int c) {
@@ -361,21 +363,21 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const uint32_t w = stage_addr(item);
         const uint32_t xa_hi = xa + (xcnt & 1) * WdSmem::xa_buf;
         wd_mma_block(tmem + 0, xa_hi, xa_hi + WdSmem::xa_buf / 2, 2 * core_col, w, w + kWdHalf, 2 * core_col, core_col, 128,
-                     idesc_fwd, 0, (valid + 15) / 16, P.passes, c > 0);
+                     idesc_fwd, 0, (valid + 15) / 16, P.passes, c > 0, leader);
       };
       auto xa_wait = [&]() {
         mbar_wait(wd_bar(smem, WdSmem::xa_full + (xcnt & 1)), (xcnt >> 1) & 1);
         tcgen05_fence_after();
       };
-      auto xa_release = [&]() { mma_commit(wd_bar(smem, WdSmem::xa_empty + (xcnt & 1))); ++xcnt; };
+      auto xa_release = [&]() { if (leader) mma_commit(wd_bar(smem, WdSmem::xa_empty + (xcnt & 1))); ++xcnt; };
       // input-gradient chunk c: G[c & 1] = delta1 . W1[:, chunk c]   (B = MN-major view of the same bytes)
       auto gemm4_chunk = [&](uint32_t item, int c) {
         const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
         const int ncols = ((valid + 15) / 16) * 16;
         const uint32_t w = stage_addr(item);
         wd_mma_block(tmem + 384 + 64 * (c & 1), a_hi, a_lo, 2 * core_col, w, w + kWdHalf, 256, 128, core_col,
-                     make_idesc_bf16(kWdM, ncols, true), 0, k_h1, P.passes, false);
-        mma_commit(wd_bar(smem, WdSmem::g_full + (c & 1)));
+                     make_idesc_bf16(kWdM, ncols, true), 0, k_h1, P.passes, false, leader);
+        if (leader) mma_commit(wd_bar(smem, WdSmem::g_full + (c & 1)));
       };
       // a 128-wide product whose A chunks are published one 16-column chunk at a time by the epilogue
       auto gemm_chunked = [&](uint32_t tmem_d, uint32_t w_hi, uint32_t w_lo, bool backward, int ksteps) {
@@ -383,10 +385,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
           tcgen05_fence_after();
           if (backward)
-            wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 256, 128, core_col, idesc_bwd, kk, kk + 1, P.passes, kk > 0);
+            wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 256, 128, core_col, idesc_bwd, kk, kk + 1, P.passes, kk > 0, leader);
           else
             wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 2 * core_col, core_col, 128, idesc_fwd, kk, kk + 1,
-                         P.passes, kk > 0);
+                         P.passes, kk > 0, leader);
         }
         // chunks beyond ksteps are still published by the epilogue: consume their phases
         for (int kk = ksteps; kk < 8; ++kk) mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
@@ -403,16 +405,16 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           ring_release(it);
           ++it;
         }
-        mma_commit(wd_bar(smem, WdSmem::acc_full));
+        if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
         for (int k = 0; k < n_unit_steps; ++k) {
           const bool last = (k == n_unit_steps - 1);
           ring_wait(it);
           ring_wait(it + 1);
           const uint32_t w2hi = stage_addr(it), w2lo = stage_addr(it + 1);
           gemm_chunked(tmem + 128, w2hi, w2lo, false, k_h1);   // z2 = h1 . W2^T
-          mma_commit(wd_bar(smem, WdSmem::acc_full));
+          if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
           gemm_chunked(tmem + 0, w2hi, w2lo, true, k_h2);      // t = delta2 . W2
-          mma_commit(wd_bar(smem, WdSmem::acc_full));
+          if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
           ring_release(it);
           ring_release(it + 1);
           it += 2;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
             if (c + 2 < NC) { ring_wait(it + c + 2); gemm4_chunk(it + c + 2, c + 2); }
           }
           it += NC;
-          if (!last) mma_commit(wd_bar(smem, WdSmem::acc_full));
+          if (!last) if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
         }
       }
       // the last commits must have landed in shared memory before the CTA may retire

@@ -301,9 +301,10 @@ __device__ __forceinline__ void tc_stage_weights(uint8_t* smem, const TcParams& 
   }
 }
 
-// one product: D[tmem_d] = A (k-major, chunks published by the epilogue) x B, B = W^T (forward) or W (backward)
+// one product: D[tmem_d] = A (k-major, chunks published by the epilogue) x B, B = W^T (forward) or W (backward).
+// Called by the whole (converged) MMA warp; `leader` = elect_one() issues.
 __device__ __forceinline__ void tc_issue_gemm(uint8_t* smem, uint32_t tmem_d, int w_hi_off, int w_lo_off, bool backward,
-                                              int ksteps, int passes, uint32_t parity) {
+                                              int ksteps, int passes, uint32_t parity, bool leader) {
   const uint32_t a_hi = smem_u32(smem + TcSmemLayout::a_hi), a_lo = smem_u32(smem + TcSmemLayout::a_lo);
   const uint32_t w_hi = smem_u32(smem + w_hi_off), w_lo = smem_u32(smem + w_lo_off);
   const uint32_t idesc = make_idesc_bf16(kTcM, kTcW, backward);
@@ -321,16 +322,19 @@ __device__ __forceinline__ void tc_issue_gemm(uint8_t* smem, uint32_t tmem_d, in
     const uint32_t b_lbo = backward ? 128 : kTcW * 16, b_sbo = backward ? kTcW * 16 : 128;
     const uint64_t ah = make_smem_desc(a_hi + a_off, kTcM * 16, 128);
     const uint64_t bh = make_smem_desc(w_hi + b_off, b_lbo, b_sbo);
-    mma_bf16(tmem_d, ah, bh, idesc, !first);
-    first = false;
-    if (passes == 3) {
-      const uint64_t al = make_smem_desc(a_lo + a_off, kTcM * 16, 128);
-      const uint64_t bl = make_smem_desc(w_lo + b_off, b_lbo, b_sbo);
-      mma_bf16(tmem_d, al, bh, idesc, true);
-      mma_bf16(tmem_d, ah, bl, idesc, true);
+    if (leader) {
+      mma_bf16(tmem_d, ah, bh, idesc, !first);
+      if (passes == 3) {
+        const uint64_t al = make_smem_desc(a_lo + a_off, kTcM * 16, 128);
+        const uint64_t bl = make_smem_desc(w_lo + b_off, b_lbo, b_sbo);
+        mma_bf16(tmem_d, al, bh, idesc, true);
+        mma_bf16(tmem_d, ah, bl, idesc, true);
+      }
     }
+    first = false;
   }
-  mma_commit(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8));
+  if (leader) mma_commit(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8));
+  __syncwarp();
 }
 
 // a thread's 32 consecutive columns of one row <-> global memory: eight 128-bit accesses when the row is 16-byte aligned

@@ -46,6 +46,19 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+// true in exactly one lane of a converged warp.  MMA-issue warps run their loops converged (all lanes wait on the mbarriers, every
+// address and descriptor is warp-uniform and lives in uniform registers) and issue under this predicate: a loop entered by a
+// single lane instead makes the compiler re-uniformise every tcgen05 operand with an ELECT / R2UR.BROADCAST / BRA.U.ANY ladder.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
