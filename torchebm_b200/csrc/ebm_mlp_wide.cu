@@ -19,10 +19,7 @@
 // complete the role warpgroup that gives its registers away), warps 4..19 = epilogue
 // (thread = one chain row x 32 hidden columns in the 128-wide phases, x 16 state columns per chunk in the E4 phase).
 // TMEM columns: [0,128) z1 / t, [128,256) z2, [256,384) act'(z1), [384,448) G even chunks, [448,512) G odd chunks.
-#include "api_common.cuh"
-#include "umma.cuh"
-#include "mlp_schedule.cuh"
-#include <cuda_bf16.h>
+#include "mlp_tc_common.cuh"   // packed fp32x2 epilogue arithmetic, bf16 hi/lo split, TMEM <-> register pairs
 
 namespace ebm {
 
@@ -84,6 +81,7 @@ struct WdParams {
   int n_steps, thin, n_kept, step_base, has_clamp;   // step_base: steps of this burst done by earlier launches
   float clamp_lo, clamp_hi;
   RowRng rng;
+  PhiloxKeys keys;    // round keys of (rng.k0, rng.k1)
   MlpSchedule sched;
   // burst-end gather fused into the final state store (last launch of a burst only): the final state of a tile is also
   // stored at element offset peer_off of every rank's peer-mapped gathered buffer, over NVLink for the remote ones.
@@ -163,6 +161,19 @@ __device__ __forceinline__ void wd_store16(uint8_t* hi_base, uint8_t* lo_base, i
       const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
       pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
     }
+    const int off = core_offset(r, col0 + oct * 8, kWdM);
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// packed form: 8 pairs = 16 consecutive columns (split2: truncated hi, rounded residual)
+__device__ __forceinline__ void wd_store16p(uint8_t* hi_base, uint8_t* lo_base, int r, int col0, const f32x2* v, bool with_lo) {
+#pragma unroll
+  for (int oct = 0; oct < 2; ++oct) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[oct * 4 + j], ph[j], pl[j], with_lo);
     const int off = core_offset(r, col0 + oct * 8, kWdM);
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     if (with_lo) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -449,9 +460,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     const int row = 32 * q + lane;
     const int hcol = 32 * cg;                       // hidden columns [hcol, hcol + 32) in the 128-wide phases
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-    const float* b1 = reinterpret_cast<const float*>(smem + WdSmem::b1) + hcol;
-    const float* b2 = reinterpret_cast<const float*>(smem + WdSmem::b2) + hcol;
-    const float* w3 = reinterpret_cast<const float*>(smem + WdSmem::w3) + hcol;
+    const f32x2* b1 = reinterpret_cast<const f32x2*>(reinterpret_cast<const float*>(smem + WdSmem::b1) + hcol);
+    const f32x2* b2 = reinterpret_cast<const f32x2*>(reinterpret_cast<const float*>(smem + WdSmem::b2) + hcol);
+    const f32x2* w3 = reinterpret_cast<const f32x2*>(reinterpret_cast<const float*>(smem + WdSmem::w3) + hcol);
     uint8_t* const a_hi = smem + WdSmem::a_hi;
     uint8_t* const a_lo = smem + WdSmem::a_lo;
     uint8_t* const xa = smem + WdSmem::xa;
@@ -504,12 +515,12 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         tcgen05_fence_after();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float v[16], s[16];
-          tmem_ld16(lane_addr + 0 + hcol + 16 * blk, v);
+          f32x2 v[8], sd[8];
+          tmem_ld16p(lane_addr + 0 + hcol + 16 * blk, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) wd_act<ACT>(v[i] + b1[16 * blk + i], v[i], s[i]);
-          tmem_st16(lane_addr + 256 + hcol + 16 * blk, s);
-          wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          for (int i = 0; i < 8; ++i) act2<ACT>(add2(v[i], b1[8 * blk + i]), v[i], sd[i]);
+          tmem_st16p(lane_addr + 256 + hcol + 16 * blk, sd);
+          wd_store16p(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
           wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
@@ -517,15 +528,15 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         tcgen05_fence_after();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float v[16];
-          tmem_ld16(lane_addr + 128 + hcol + 16 * blk, v);
+          f32x2 v[8];
+          tmem_ld16p(lane_addr + 128 + hcol + 16 * blk, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float hh, dh;
-            wd_act<ACT>(v[i] + b2[16 * blk + i], hh, dh);
-            v[i] = w3[16 * blk + i] * dh;
+          for (int i = 0; i < 8; ++i) {
+            f32x2 hh, dh;
+            act2<ACT>(add2(v[i], b2[8 * blk + i]), hh, dh);
+            v[i] = mul2(dh, w3[8 * blk + i]);
           }
-          wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          wd_store16p(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
           wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E3: t -> delta1 = t * act'(z1) (A of every GEMM4 chunk)
@@ -534,12 +545,12 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         tmem_st_wait();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          float v[16], s[16];
-          tmem_ld16(lane_addr + 0 + hcol + 16 * blk, v);
-          tmem_ld16(lane_addr + 256 + hcol + 16 * blk, s);
+          f32x2 v[8], sd[8];
+          tmem_ld16p_nowait(lane_addr + 0 + hcol + 16 * blk, v);
+          tmem_ld16p(lane_addr + 256 + hcol + 16 * blk, sd);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= s[i];
-          wd_store16(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          for (int i = 0; i < 8; ++i) v[i] = mul2(v[i], sd[i]);
+          wd_store16p(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
           wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E4: per 64-column chunk: G_c -> Langevin update of the state chunk -> global + A operand of GEMM1'_c
@@ -552,7 +563,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           // covers its latency
           float xc[16];
           if (active) wd_load_x16(xsrc, xrow, col0, P.d, rv, vec, xc);
-          float eps[16];
+          f32x2 eps[8];
           if (active) {
             const long long li0 = grow * P.d + col0;
             if (P.rng.mode == 2 && P.d % 4 == 0 && col0 + 16 <= P.d) {
@@ -560,48 +571,52 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
               for (int q4 = 0; q4 < 4; ++q4) {
                 const uint64_t qi = (uint64_t)(li0 + 4 * q4) >> 2;
                 const uint4 w = philox4x32_10((uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)ctr_base,
-                                              (uint32_t)(ctr_base >> 32), P.rng.k0, P.rng.k1);
-                const float4 nn = normal4_fast(w);
-                eps[4 * q4] = nn.x; eps[4 * q4 + 1] = nn.y; eps[4 * q4 + 2] = nn.z; eps[4 * q4 + 3] = nn.w;
+                                              (uint32_t)(ctr_base >> 32), P.keys);
+                normal4_fast_packed(w, eps[2 * q4], eps[2 * q4 + 1]);
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const bool in = rv && (col0 + i) < P.d;
-                float ev = 0.0f;
-                if (in) {
-                  if (P.rng.mode == 0) {
-                    ev = P.noise[(long long)k * (P.n * P.d) + li0 + i];
-                  } else {
-                    ev = normal_for_element_call(P.rng.k0, P.rng.k1, ctr_base, P.rng.T, P.rng.mode, (uint64_t)(li0 + i));
-                  }
+              for (int i = 0; i < 8; ++i) {
+                float ev[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int col = 2 * i + u;
+                  const bool in = rv && (col0 + col) < P.d;
+                  ev[u] = 0.0f;
+                  if (in) ev[u] = (P.rng.mode == 0) ? P.noise[(long long)k * (P.n * P.d) + li0 + col]
+                                                    : normal_for_element_call(P.rng.k0, P.rng.k1, ctr_base, P.rng.T, P.rng.mode, (uint64_t)(li0 + col));
                 }
-                eps[i] = ev;
+                eps[i] = pack2(ev[0], ev[1]);
               }
             }
           }
           mbar_wait(wd_bar(smem, WdSmem::g_full + (c & 1)), (g_par >> (c & 1)) & 1);
           g_par ^= 1u << (c & 1);
           tcgen05_fence_after();
+          f32x2 X[8];
           if (active) {
-            float g[16];
-            tmem_ld16(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
+            f32x2 g[8];
+            tmem_ld16p(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
+            const float c12 = c1 * c2;
+            // x' = (x - h g) + c2 c1 eps (base_integrator.py:728-729) on packed pairs; the fused roundings are within this
+            // kernel's 2e-5 class
+#pragma unroll
+            for (int i = 0; i < 8; ++i) X[i] = fma2(eps[i], c12, fma2(g[i], -h, pack2(xc[2 * i], xc[2 * i + 1])));
             if (P.has_clamp) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float x1 = __fsub_rn(xc[i], __fmul_rn(h, g[i]));
-                xc[i] = clamp_torch(__fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1))), P.clamp_lo, P.clamp_hi);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float x1 = __fsub_rn(xc[i], __fmul_rn(h, g[i]));
-                xc[i] = __fadd_rn(x1, __fmul_rn(c2, __fmul_rn(eps[i], c1)));
+              for (int i = 0; i < 8; ++i) {
+                float xa_, xb_;
+                unpack2(X[i], xa_, xb_);
+                X[i] = pack2(clamp_torch(xa_, P.clamp_lo, P.clamp_hi), clamp_torch(xb_, P.clamp_lo, P.clamp_hi));
               }
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) unpack2(X[i], xc[2 * i], xc[2 * i + 1]);
             if (col0 + 16 > P.d) {  // ragged last block: columns beyond the state stay exactly zero
 #pragma unroll
               for (int i = 0; i < 16; ++i) xc[i] = (col0 + i) < P.d ? xc[i] : 0.0f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) X[i] = pack2(xc[2 * i], xc[2 * i + 1]);
             }
           }
           // publish the new chunk to the tensor core first (GEMM1' of the next step is on the critical path), then
@@ -611,7 +626,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           ++xcnt;
           if (active) {
             uint8_t* const xa_hi = xa + xb * WdSmem::xa_buf;
-            wd_store16(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, xc, with_lo);
+            wd_store16p(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, X, with_lo);
           }
           wd_publish(xa_full + 8 * xb);
           if (active) {
@@ -884,6 +899,7 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     P.rng.k0 = (uint32_t)c.seed ^ kNativeTag0; P.rng.k1 = (uint32_t)(c.seed >> 32) ^ kNativeTag1;
     P.rng.ctr_step = 1;
   }
+  philox_expand_keys(P.keys, P.rng.k0, P.rng.k1);
   // the weights may have changed since the last burst (training loop): re-split them on the caller's stream
   {
     const int items = (P.nc * kWdH * (kWdChunk / 8)) + kWdH * (kWdH / 8);
