@@ -45,6 +45,10 @@ WORKLOADS = {
     "c1": ("LangevinDynamics GaussianModel(mean=0, cov=[[1,.8],[.8,1]]) dim=2 n_chains=1024 k=100 step_size=0.01 "
            "(examples/10-sampling/01-mcmc/01-langevin-101; the reference's own CPU-runnable case)", 1024, 2, 100),
     "c2": ("LangevinDynamics DoubleWell(2.0,1.0) dim=128 n_chains=65536 k=500 step_size=0.01 noise_scale=1.0", 65536, 128, 500),
+    # C2 with the whole trajectory kept (return_trajectory=True, thin=1): the one configuration where the burst really
+    # streams to HBM every step -- 4*D bytes per chain-step of trajectory + the state once per burst
+    "c2_traj": ("LangevinDynamics DoubleWell(2.0,1.0) dim=128 n_chains=65536 k=500, return_trajectory=True thin=1 "
+                "(16.8 GB trajectory written per burst)", 65536, 128, 500),
     "mlp128": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01", 65536, 128, 100),
     "mlp128_fp32": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (fp32 FFMA kernel)", 65536, 128, 100),
     "mlp128_bf16": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (single-pass bf16)", 65536, 128, 100),
@@ -262,6 +266,19 @@ def make_workload(name: str, n_local: int, dev, rng: str = "torch"):
             return 1, out
 
         return step, desc, model, 8 * d, k
+    if name == "c2_traj":
+        model = te.DoubleWellModel(2.0, 1.0)
+        desc = te.energy_descriptor(model, d, dev)
+        inc = ops.rng_consumed_langevin(dev, n_local * d, k, mode)
+        traj = torch.empty(n_local, k, d, device=dev)   # [n, n_kept, d] like the reference's trajectory tensor
+
+        def step(x, out, it, kev=None):
+            if kev: kev[0].record()
+            ops.langevin_burst(desc, x, k, [0.01], [1.0], rng_mode=mode, seed=1234, offset=it * inc, out=out, traj=traj, thin=1)
+            if kev: kev[1].record()
+            return 1, out
+
+        return step, desc, model, 4 * d + 8.0 * d / k, k
     if name == "c1":
         model = te.GaussianModel(torch.zeros(2), torch.tensor([[1.0, 0.8], [0.8, 1.0]])).to(dev)
         desc = te.energy_descriptor(model, d, dev)
@@ -568,7 +585,10 @@ def compact(res, peaks, peak_kind):
     r = roofline_of(res, peaks, peak_kind)
     out = {"value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"], "kernel_ms": res["kernel_ms"],
            "workload": res["desc"], "rng": res["rng"],
-           "roofline": {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac") if k in r}}
+           "roofline": {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "issue_frac") if k in r}}
+    if res["workload"] == "c2_traj":   # the one line whose GB/s are bytes that really cross the HBM interface
+        out["roofline"]["note"] = ("achieved = (8*D*N state + 4*D*N*K trajectory bytes) / kernel time: real DRAM traffic, not the "
+                                   "streaming model")
     if res["gather_check"] is not None:
         out["gather_check"] = res["gather_check"]
         out["collective"] = res["collective"]
@@ -592,8 +612,9 @@ def run_ours(args):
         # caps the torch-layout strong scaling at 86.5 % for 65 536 / N chains
         extra["native_rng"] = measure("c2", args.steps, args.warmup, rank, world, local, rng="native", nccl_gather=args.nccl_gather)
         sec_steps = max(5, min(args.steps, 10))
-        secondary = ["mlp128", "c3", "c4"] if world == 1 else ["c5"]
-        extra["secondary"] = {w: measure(w, sec_steps, 3, rank, world, local, rng="native") for w in secondary}
+        secondary = ["mlp128", "c3", "c4", "hmc_mlp128", "c2_traj"] if world == 1 else ["c5"]
+        extra["secondary"] = {w: measure(w, sec_steps, 3, rank, world, local, rng="torch" if w == "c2_traj" else "native")
+                              for w in secondary}
     if rank != 0:
         return
     peaks, peak_kind = measured_peaks()
@@ -642,7 +663,9 @@ def run_ours(args):
             line["triton_poc"] = triton_poc_baseline(dev, ref)
         if "secondary" in line:
             for w in line["secondary"]:
-                base = (torch_cuda_hmc_baseline(dev, w, ref) if w == "c4" else torch_cuda_baseline(dev, w, ref=ref))
+                if w == "c2_traj":   # (the reference keeps a trajectory by copying the state every step: same per-step cost as c2)
+                    continue
+                base = (torch_cuda_hmc_baseline(dev, w, ref) if w in ("c4", "hmc_mlp128") else torch_cuda_baseline(dev, w, ref=ref))
                 line["secondary"][w]["torch_cuda_baseline"] = {"value": base["value"], "what": base["what"], "sample": base["sample"]}
                 line["secondary"][w]["vs_torch_cuda"] = line["secondary"][w]["value"] / base["value"]
     print(json.dumps(line))

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 7
+#define EBM_ABI_VERSION 8
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -252,6 +252,13 @@ int ebm_hmc_burst_diag_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
                            const float* noise_p, const float* noise_u, float* traj, int32_t thin, double* diag_ws,
                            float* scratch, int32_t* accept_count, float* diag_mean, float* diag_var, float* diag_energy,
                            float* diag_accept, void* stream);
+
+/* Effective sample size of n_chains chains of n samples each (chains[n_chains, n], contiguous): replaces
+ * `_ess_from_chain` of the reference's benchmark harness (benchmarks/registry.py:348-365), which the harness applies to
+ * the energy chain of a sampler's diagnostics (:766-770).  Same estimator (centred chain, autocovariances, lags summed up
+ * to the first negative one, ESS = n / max(1 + 2 sum rho_k, 1); n for chains shorter than 2 or of zero variance); the
+ * autocovariances are direct fp64 sums instead of an fp32 FFT.  ess_out[n_chains]. */
+int ebm_ess_f32(const float* chains, int64_t n_chains, int64_t n, float* ess_out, void* stream);
 
 /* Fill out[numel] with the TORCH- or NATIVE-layout normal (kind 0) / uniform (kind 1) stream at
  * (seed, offset): test hook that exposes exactly what the fused kernels draw. */

@@ -6,6 +6,8 @@ energies (what the CUDA kernels implement); stated tolerances for the closed for
 a reduction (Gaussian, MoG, MLP).
 """
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -177,3 +179,18 @@ def test_heun_oracle_matches_reference_golden(name):
         out = olang.sample(en, g["x0"], int(g["k"]), float(g["h"]), float(g["ns"]), noise=g["noise"], scheme="heun",
                            closed_form=closed, **kw)
         assert torch.equal(out, g["out"])
+
+
+def test_ess_oracle_matches_reference_golden():
+    """oracle/ess.py restates benchmarks/registry.py:348-365; the goldens come from the unmodified function."""
+    import numpy as np
+
+    from oracle import ess as oess
+
+    z = np.load(os.path.join(C.GOLDEN, "ess_chains.npz"))
+    names = [k[6:] for k in z.files if k.startswith("chain_")]
+    assert len(names) >= 10
+    for name in names:
+        chain = torch.from_numpy(z["chain_" + name])
+        assert oess.ess_from_chain(chain) == float(z["ess_" + name]), name
+        assert oess.ess_direct(z["chain_" + name]) == pytest.approx(float(z["ess_" + name]), rel=1e-5), name

@@ -15,6 +15,7 @@ from . import _lib
 from ._ref import reference as _reference
 from .core import (BaseModel, DoubleWellModel, GaussianModel, HarmonicModel, MixtureOfGaussiansModel, MLPEnergy,
                    RastriginModel, energy_descriptor, mark_mlp_energy)
+from .diagnostics import ess_from_chain, ess_from_diagnostics
 from .integrators import HeunIntegrator, energy_drift
 
 REFERENCE_DERIVED = _reference() is not None
@@ -43,5 +44,6 @@ __all__ = [
     "GaussianModel", "HarmonicModel", "LinearScheduler", "MixtureOfGaussiansModel", "MLPEnergy", "RastriginModel",
     "energy_descriptor", "mark_mlp_energy", "EulerMaruyamaIntegrator", "HeunIntegrator", "LeapfrogIntegrator", "energy_drift",
     "BaseContrastiveDivergence", "ContrastiveDivergence", "BaseSampler", "HamiltonianMonteCarlo", "LangevinDynamics",
-    "GradientDescentSampler", "NesterovSampler", "REFERENCE_DERIVED", "install", "uninstall",
+    "GradientDescentSampler", "NesterovSampler", "REFERENCE_DERIVED", "install", "uninstall", "ess_from_chain",
+    "ess_from_diagnostics",
 ]

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # EBM_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); still no fallback of any kind
 LIB_PATH = os.environ.get("EBM_B200_LIB") or os.path.join(HERE, "lib", "libebm_b200.so")
 
-EBM_ABI_VERSION = 7
+EBM_ABI_VERSION = 8
 
 ENERGY_DOUBLE_WELL, ENERGY_HARMONIC, ENERGY_RASTRIGIN, ENERGY_GAUSSIAN, ENERGY_MOG, ENERGY_MLP = range(6)
 ACT_SILU, ACT_TANH, ACT_RELU, ACT_SOFTPLUS = range(4)
@@ -88,6 +88,7 @@ PROTOTYPES = {
                                               _P, _P, _P, _P, _P, _P]),
     "ebm_hmc_burst_diag_f32": (C.c_int, [_DESC, _P, _P, _I64, _I32, _I32, _PD, _I32, _I32, _F64, _P, _I32, _U64, _U64, _P, _P, _P,
                                          _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ebm_ess_f32": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "ebm_rng_fill_f32": (C.c_int, [_P, _I64, _I32, _I32, _U64, _U64, _P]),
 }
 

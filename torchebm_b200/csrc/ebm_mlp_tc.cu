@@ -352,9 +352,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
     const int col_base = kTcCols * cq;
     const int first_chunk = col_base / 16;
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + col_base;
-    const float* b1 = reinterpret_cast<const float*>(smem + TcSmemLayout::b1) + col_base;
-    const float* b2 = reinterpret_cast<const float*>(smem + TcSmemLayout::b2) + col_base;
-    const float* w3 = reinterpret_cast<const float*>(smem + TcSmemLayout::w3) + col_base;
+    const f32x2* b1 = reinterpret_cast<const f32x2*>(smem + TcSmemLayout::b1 + 4 * col_base);
+    const f32x2* b2 = reinterpret_cast<const f32x2*>(smem + TcSmemLayout::b2 + 4 * col_base);
+    const f32x2* w3 = reinterpret_cast<const f32x2*>(smem + TcSmemLayout::w3 + 4 * col_base);
     float* part = reinterpret_cast<float*>(smem + TcSmemLayout::hmc_part);   // [2][4 kinds][4 cq][128 rows]
     const uint32_t acc_bar = smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8);
     const bool with_lo = P.passes == 3;
@@ -446,52 +446,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
         }
         for (int l = 0; l <= L; ++l) {
           const bool want_e = (l == 0) || (l == L);
-          // E1: z1 -> h1 ; act'(z1) -> TMEM [256, 384)
+          // E1: z1 -> h1 ; act'(z1) -> TMEM [256, 384)   (E1-E3 on packed fp32x2 pairs, as in langevin_mlp_tc_kernel)
           mbar_wait(acc_bar, parity); parity ^= 1;
           tcgen05_fence_after();
+          f32x2 acc[16];
+          tmem_ld32p(lane_addr + 0, acc);
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
-            float v[16], sd[16];
-            tmem_ld16(lane_addr + 0 + 16 * blk, v);
+            f32x2 sd[8];
+            f32x2* v = acc + 8 * blk;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) act_fast<ACT>(v[i] + b1[16 * blk + i], v[i], sd[i]);
-            tmem_st16(lane_addr + 256 + 16 * blk, sd);
-            store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+            for (int i = 0; i < 8; ++i) act2<ACT>(add2(v[i], b1[8 * blk + i]), v[i], sd[i]);
+            tmem_st16p(lane_addr + 256 + 16 * blk, sd);
+            store_a_16p(smem, row, col_base + 16 * blk, v, with_lo);
             tcgen05_fence_before();
             signal_one(smem, first_chunk + blk, lane);
           }
           // E2: z2 -> delta2 = w3 * act'(z2) ; energy partial w3 . act(z2)
           mbar_wait(acc_bar, parity); parity ^= 1;
           tcgen05_fence_after();
-          float esum = 0.0f;
+          f32x2 esum2 = pack2(0.0f, 0.0f);
+          tmem_ld32p(lane_addr + 128, acc);
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
-            float v[16];
-            tmem_ld16(lane_addr + 128 + 16 * blk, v);
+            f32x2* v = acc + 8 * blk;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float hh, dh;
-              act_fast<ACT>(v[i] + b2[16 * blk + i], hh, dh);
-              esum = fmaf(w3[16 * blk + i], hh, esum);
-              v[i] = w3[16 * blk + i] * dh;
+            for (int i = 0; i < 8; ++i) {
+              f32x2 hh, dh;
+              act2<ACT>(add2(v[i], b2[8 * blk + i]), hh, dh);
+              if (want_e) esum2 = fma2(w3[8 * blk + i], hh, esum2);
+              v[i] = mul2(dh, w3[8 * blk + i]);
             }
-            store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+            store_a_16p(smem, row, col_base + 16 * blk, v, with_lo);
             tcgen05_fence_before();
             signal_one(smem, first_chunk + blk, lane);
           }
-          if (want_e) { if (l == 0) e0p[row] = esum; else e1p[row] = esum; }
+          if (want_e) {
+            float ea, eb;
+            unpack2(esum2, ea, eb);
+            if (l == 0) e0p[row] = ea + eb; else e1p[row] = ea + eb;
+          }
           // E3: t -> delta1 = t * act'(z1)
           mbar_wait(acc_bar, parity); parity ^= 1;
           tcgen05_fence_after();
           tmem_st_wait();
+          tmem_ld32p_nowait(lane_addr + 0, acc);
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
-            float v[16], sd[16];
-            tmem_ld16(lane_addr + 0 + 16 * blk, v);
-            tmem_ld16(lane_addr + 256 + 16 * blk, sd);
+            f32x2 sd[8];
+            f32x2* v = acc + 8 * blk;
+            tmem_ld16p(lane_addr + 256 + 16 * blk, sd);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= sd[i];
-            store_a_16(smem, row, col_base + 16 * blk, v, with_lo);
+            for (int i = 0; i < 8; ++i) v[i] = mul2(v[i], sd[i]);
+            store_a_16p(smem, row, col_base + 16 * blk, v, with_lo);
             tcgen05_fence_before();
             signal_one(smem, first_chunk + blk, lane);
           }
@@ -501,10 +508,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
           float ksum = 0.0f;
           // three straight-line variants: first evaluation (top of step 1), middle (bottom of step l + top of step l+1),
           // last (bottom of step L + kinetic energy) -- `l` is uniform, so this only removes per-element predication
-          auto e4 = [&](auto first_c, auto last_c) {
+          auto e4 = [&](auto first_c, auto last_c, unsigned todo) {
             constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk) {
+              if (!((todo >> blk) & 1)) continue;   // (warp-uniform only for the mass kinds; per-thread after the detector)
               float g[16], pv[16];
               tmem_ld16(lane_addr + 128 + 16 * blk, g);
               tmem_ld16(lane_addr + 384 + 16 * blk, pv);
@@ -536,9 +544,74 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
               }
             }
           };
-          if (l == 0) e4(std::true_type{}, std::false_type{});
-          else if (l < L) e4(std::false_type{}, std::false_type{});
-          else e4(std::false_type{}, std::true_type{});
+          // Unit mass (the reference's default): the same update on packed pairs.  The safe-mode clamp and the sanitising
+          // leave finite values below 1e6 untouched, so the fast path only has to DETECT anything else -- v * 0 accumulated
+          // over a 16-column block is 0 unless some v is NaN / inf, one packed FMA per pair -- and the rows of a block that
+          // trips the detector (a diverged chain) go through the exact scalar code above instead.  Kicks and drift are fused
+          // multiply-adds here: their rounding is far inside the split-operand force error.
+          auto e4_fast = [&](auto first_c, auto last_c) -> unsigned {
+            constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
+            const f32x2 zero2 = pack2(0.0f, 0.0f);
+            unsigned todo = 0;
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+              f32x2 G[8], Pm[8], Xn[8];
+              tmem_ld16p_nowait(lane_addr + 128 + 16 * blk, G);
+              tmem_ld16p(lane_addr + 384 + 16 * blk, Pm);
+              f32x2 det = zero2;
+              float kblk = 0.0f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float ga, gb;
+                unpack2(G[i], ga, gb);
+                det = fma2(G[i], zero2, det);
+                const f32x2 F = pack2(fminf(fmaxf(-ga, -kSafeClamp), kSafeClamp), fminf(fmaxf(-gb, -kSafeClamp), kSafeClamp));
+                f32x2 Xv = pack2(x[16 * blk + 2 * i], x[16 * blk + 2 * i + 1]);
+                f32x2 Pv = Pm[i];
+                if (!kFirst) {                     // bottom of step l: second half kick; sanitising = detection only
+                  Pv = fma2(F, half_h, Pv);
+                  det = fma2(Xv, zero2, det);
+                  det = fma2(Pv, zero2, det);
+                }
+                if (!kLast) {                      // top of step l+1: first half kick and drift
+                  Pv = fma2(F, half_h, Pv);
+                  Xv = fma2(Pv, h, Xv);
+                } else {
+                  float pa, pb;
+                  unpack2(Pv, pa, pb);
+                  kblk = fmaf(pa, pa, fmaf(pb, pb, kblk));
+                }
+                Xn[i] = Xv;
+                Pm[i] = Pv;
+              }
+              float da, db;
+              unpack2(det, da, db);
+              const bool clean = (da + db == 0.0f);
+              // the tensor core needs the chunk of every row: rows that tripped the detector publish from the exact path
+              if (!__all_sync(0xffffffffu, clean)) { todo |= 1u << blk; continue; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) unpack2(Xn[i], x[16 * blk + 2 * i], x[16 * blk + 2 * i + 1]);
+              if (kLast) ksum += kblk;
+              if (!kLast) {
+                tmem_st16p(lane_addr + 384 + 16 * blk, Pm);
+                store_a_16p(smem, row, col_base + 16 * blk, Xn, with_lo);
+                tcgen05_fence_before();
+                signal_one(smem, first_chunk + blk, lane);
+              }
+            }
+            return todo;
+          };
+          unsigned todo = 3;
+          if (H.mass.kind == 0) {
+            if (l == 0) todo = e4_fast(std::true_type{}, std::false_type{});
+            else if (l < L) todo = e4_fast(std::false_type{}, std::false_type{});
+            else todo = e4_fast(std::false_type{}, std::true_type{});
+          }
+          if (todo) {
+            if (l == 0) e4(std::true_type{}, std::false_type{}, todo);
+            else if (l < L) e4(std::false_type{}, std::false_type{}, todo);
+            else e4(std::false_type{}, std::true_type{}, todo);
+          }
           if (l == L) k1p[row] = ksum;
         }
         // all four column quarters of every row have written their partial sums

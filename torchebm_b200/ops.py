@@ -323,6 +323,22 @@ def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Option
     return out, int(new_ptr.value)
 
 
+def ess(chains: torch.Tensor) -> torch.Tensor:
+    """Effective sample size of every row of `chains[n_chains, n]` (or of one 1-D chain) on the device: the estimator of
+    benchmarks/registry.py:348-365.  Returns a float32 tensor of shape `[n_chains]` (0-d for a 1-D chain); no sync."""
+    chains = _req(chains, "chains")
+    one = chains.ndim == 1
+    if one:
+        chains = chains.unsqueeze(0)
+    if chains.ndim != 2 or chains.shape[1] < 1 or chains.shape[0] < 1:
+        raise ValueError("chains must be a non-empty [n_chains, n] tensor or a 1-D chain")
+    out = torch.empty(chains.shape[0], dtype=torch.float32, device=chains.device)
+    with torch.cuda.device(chains.device):
+        rc = _lib.load().ebm_ess_f32(chains.data_ptr(), chains.shape[0], chains.shape[1], out.data_ptr(), _stream(chains.device))
+    _lib.check(rc, "ebm_ess_f32")
+    return out[0] if one else out
+
+
 def rng_fill(numel: int, device, rng_mode: int, kind: int, seed: int, offset: int) -> torch.Tensor:
     out = torch.empty(numel, dtype=torch.float32, device=device)
     with torch.cuda.device(out.device):
