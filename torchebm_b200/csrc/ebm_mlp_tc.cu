@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
 // in x_out.  Deviation from the reference in one corner: when safe-mode sanitising rewrites a NaN/inf coordinate the
 // reference recomputes the force at the sanitised state before the next step; here the carried force is kept.
 struct TcHmcParams {
-  TcParams T;      // weights, widths, passes, schedule; T.n_steps = proposals of this launch * (L + 1)
+  MlpSchedule sched;   // balanced (tile, proposal) split (the copy the kernel reads; T.sched is unused here)
+  TcParams T;          // weights, widths, passes; T.n_steps = proposals of this launch * (L + 1)
   HmcParams H;
 };
 
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
   }
   // work quantum = one proposal of one tile: a tile's proposals may be split between two CTAs (mlp_schedule.cuh); only
   // the chain state crosses the split (momentum, energy and force are rebuilt at the top of every proposal)
-  if (threadIdx.x == 32) mlp_units_compute(P.sched, H.n_prop, reinterpret_cast<volatile MlpUnits*>(smem + TcSmemLayout::units));
+  if (threadIdx.x == 32) mlp_units_compute(Q.sched, H.n_prop, reinterpret_cast<volatile MlpUnits*>(smem + TcSmemLayout::units));
   if (warp == 0) tmem_alloc(smem_u32(smem + TcSmemLayout::tmem_slot), 512);
   fence_proxy_async();
   tcgen05_fence_before();
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
       const long long grow = (long long)tile * kTcM + row;
       const bool rv = grow < H.n;
       const int s0 = mlp_unit_s0(units, tile), s1 = mlp_unit_s1(units, tile, H.n_prop);
-      if (s0 > 0) mlp_unit_acquire(P.sched, kTcEpiWarps);   // earlier proposals of this tile ran on another CTA
+      if (s0 > 0) mlp_unit_acquire(Q.sched, kTcEpiWarps);   // earlier proposals of this tile ran on another CTA
       float x[kTcCols];
       tc_load_row32(s0 == 0 ? H.x_in : H.x_out, grow, H.d, col_base, rv, x);
       store_a_cols(smem, row, col_base, x, with_lo);
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
       }
       tc_store_row32(H.x_out, grow, H.d, col_base, rv, x);
       if (rv && H.energy_out && cq == 0 && s1 == H.n_prop) H.energy_out[grow] = clamp_torch(e_final, -1e10f, 1e10f);
-      if (s1 < H.n_prop) mlp_unit_release(P.sched);   // the rest of this tile's proposals run on the next CTA
+      if (s1 < H.n_prop) mlp_unit_release(Q.sched);   // the rest of this tile's proposals run on the next CTA
     }
   }
   tcgen05_fence_before();
@@ -686,16 +687,16 @@ int hmc_mlp_tc_launch(const EbmEnergyDesc* e, const HmcParams& H, const HStepTab
   const int grid = (int)(tiles < sms ? tiles : sms);
   int* flags = reinterpret_cast<int*>(const_cast<float*>(e->buf[6]));  // NULL: whole tiles per CTA
   if (flags) {
-    int rc0 = mlp_schedule_setup(P.sched, tiles, H.n_prop, grid, flags, st);
+    int rc0 = mlp_schedule_setup(Q.sched, tiles, H.n_prop, grid, flags, st);
     if (rc0) return rc0;
   } else {
-    mlp_schedule_whole_tiles(P.sched, tiles, H.n_prop, grid);
+    mlp_schedule_whole_tiles(Q.sched, tiles, H.n_prop, grid);
   }
 #define CALL(A)                                                                                                  \
   {                                                                                                              \
     auto kern = hmc_mlp_tc_kernel<A>;                                                                            \
     EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmemLayout::hmc_total));  \
-    kern<<<grid, kTcThreads, TcSmemLayout::hmc_total, st>>>(Q, tab);                                             \
+    EBM_CUDA(mlp_launch_persistent(kern, grid, kTcThreads, TcSmemLayout::hmc_total, st, Q, tab, tiles, H.n_prop, grid)); \
   }
   switch (e->activation) {
     case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;
@@ -774,7 +775,7 @@ int langevin_mlp_tc1_dispatch(const LangevinCall& c, int passes) {
   {                                                                                                           \
     auto kern = passes == 3 ? langevin_mlp_tc_kernel<A, true> : langevin_mlp_tc_kernel<A, false>;             \
     EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmemLayout::total));   \
-    kern<<<grid, kTcThreads, TcSmemLayout::total, c.st>>>(P, tab);                                            \
+    EBM_CUDA(mlp_launch_persistent(kern, grid, kTcThreads, TcSmemLayout::total, c.st, P, tab, tiles, chunk, grid)); \
   }
     switch (e->activation) {
       case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;

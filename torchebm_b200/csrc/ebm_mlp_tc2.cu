@@ -498,11 +498,7 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.noise = c.noise ? c.noise + (long long)done * numel : nullptr;
     P.rng.ctr_base = c.offset / 4 + (unsigned long long)done * P.rng.ctr_step;
     P.step_base = done;
-    // The balanced split makes a worker spin on its predecessor's flag, which is only safe when every CTA of the grid is
-    // resident at once: the launch is cooperative (the driver refuses it otherwise), and any failure to get that falls
-    // back to whole tiles per worker, which needs no hand-over.
-    bool balanced = flags != nullptr;
-    if (balanced) {
+    if (flags) {   // balanced split (co-residency is taken care of by the cooperative launch, mlp_schedule.cuh)
       int rc0 = mlp_schedule_setup(P.sched, tiles, chunk, workers, flags, c.st);
       if (rc0) return rc0;
     } else {
@@ -512,22 +508,7 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
   {                                                                                                           \
     auto kern = passes == 3 ? langevin_mlp_tc2_kernel<A, true> : langevin_mlp_tc2_kernel<A, false>;           \
     EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem::total));         \
-    cudaLaunchConfig_t cfg;                                                                                   \
-    memset(&cfg, 0, sizeof(cfg));                                                                             \
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kT2Threads); cfg.dynamicSmemBytes = T2Smem::total;          \
-    cfg.stream = c.st;                                                                                        \
-    cudaLaunchAttribute attr[1];                                                                              \
-    attr[0].id = cudaLaunchAttributeCooperative;                                                              \
-    attr[0].val.cooperative = 1;                                                                              \
-    cfg.attrs = attr; cfg.numAttrs = balanced ? 1 : 0;                                                        \
-    cudaError_t lerr = cudaLaunchKernelEx(&cfg, kern, P, tab);                                                \
-    if (lerr != cudaSuccess && balanced) {                                                                    \
-      (void)cudaGetLastError();                                                                               \
-      mlp_schedule_whole_tiles(P.sched, tiles, chunk, workers);                                               \
-      cfg.numAttrs = 0;                                                                                       \
-      lerr = cudaLaunchKernelEx(&cfg, kern, P, tab);                                                          \
-    }                                                                                                         \
-    if (lerr != cudaSuccess) { set_error("langevin_mlp_tc2_kernel: launch failed: %s", cudaGetErrorString(lerr)); return (int)lerr; } \
+    EBM_CUDA(mlp_launch_persistent(kern, grid, kT2Threads, T2Smem::total, c.st, P, tab, tiles, chunk, workers)); \
   }
     switch (e->activation) {
       case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;

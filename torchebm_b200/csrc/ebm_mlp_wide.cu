@@ -941,7 +941,7 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
   {                                                                                                        \
     auto kern = langevin_mlp_wide_kernel<A>;                                                               \
     EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WdSmem::total));      \
-    kern<<<grid, kWdThreads, WdSmem::total, c.st>>>(P, tab);                                               \
+    EBM_CUDA(mlp_launch_persistent(kern, grid, kWdThreads, WdSmem::total, c.st, P, tab, tiles, chunk, grid)); \
   }
     switch (e->activation) {
       case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace ebm {
 
@@ -89,6 +90,36 @@ inline void mlp_schedule_whole_tiles(MlpSchedule& s, long long tiles, int k_step
   s.rem = (int)(tiles % grid);
   s.gran = k_steps;
   s.flags = nullptr;
+}
+
+
+// host: launch a persistent kernel `kern(P, tab)`.  With the balanced split (P.sched.gran == 1) a worker spin-waits on
+// its predecessor's flag, which is only safe when every CTA of the grid is resident at once -- not guaranteed when other
+// kernels share the device (a gather on another stream, a second burst).  The launch is therefore cooperative: the
+// driver co-schedules the whole grid or refuses, and a refusal falls back to whole tiles per worker (no hand-over).
+template <class Kern, class Params, class Table>
+inline cudaError_t mlp_launch_persistent(Kern kern, int grid, int threads, size_t smem, cudaStream_t st, Params& P,
+                                         const Table& tab, long long tiles, int k_steps, int workers) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  const bool balanced = P.sched.gran == 1 && P.sched.flags != nullptr;
+  cfg.numAttrs = balanced ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kern, P, tab);
+  if (err != cudaSuccess && balanced) {
+    (void)cudaGetLastError();
+    mlp_schedule_whole_tiles(P.sched, tiles, k_steps, workers);
+    cfg.numAttrs = 0;
+    err = cudaLaunchKernelEx(&cfg, kern, P, tab);
+  }
+  return err;
 }
 
 }  // namespace ebm

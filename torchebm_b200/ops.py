@@ -31,6 +31,24 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _bind_workspace(desc: EnergyDescriptor, device) -> None:
+    """The MLP workspace (hand-over flags of the balanced work split; for wide states the re-split weights) must not be
+    shared by bursts that run concurrently, so it is keyed by (device, stream) and resolved HERE, for the stream the
+    launch goes to -- a descriptor built once and launched on two streams gets two workspaces.  A descriptor whose
+    workspace pointer was cleared (whole-tile scheduling, tests) stays that way."""
+    if desc.kind != "mlp" or not desc.c.buf[6]:
+        return
+    from .core import _mlp_workspace
+
+    nbytes = int(_lib.load().ebm_workspace_bytes(C.byref(desc.c)))
+    if nbytes <= 0:
+        return
+    ws = _mlp_workspace(device, nbytes)
+    if desc.c.buf[6] != ws.data_ptr():
+        desc.c.buf[6] = ws.data_ptr()
+        desc.keep.append(ws)
+
+
 def device_index(device) -> int:
     device = torch.device(device)
     return torch.cuda.current_device() if device.index is None else device.index
@@ -107,6 +125,7 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
     hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
     cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
     heun = scheme != "euler_maruyama"
+    _bind_workspace(desc, x.device)
     with torch.cuda.device(x.device):
         if diag is not None and n_steps // thin > 0:
             ws = torch.empty((n_steps // thin) * (2 * desc.dim + 2), dtype=torch.float64, device=x.device)
@@ -138,6 +157,7 @@ def langevin_burst_gather(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int,
     hs, ns = _lib.doubles(list(step_sizes)), _lib.doubles(list(noise_scales))
     cl = (C.c_float * 2)(clamp[0], clamp[1]) if clamp is not None else None
     peers = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    _bind_workspace(desc, x.device)
     with torch.cuda.device(x.device):
         rc = _lib.load().ebm_langevin_burst_gather_f32(
             C.byref(desc.c), x.data_ptr(), out.data_ptr(), x.shape[0], int(n_steps), hs, ns, len(step_sizes), cl,
@@ -214,6 +234,7 @@ def hmc_burst(desc: EnergyDescriptor, x: torch.Tensor, n_proposals: int, n_leapf
     assert len(step_sizes) in (1, n_proposals)
     hs = _lib.doubles(list(step_sizes))
     kind, ms, mv = _mass_args(mass, x.device)
+    _bind_workspace(desc, x.device)
     with torch.cuda.device(x.device):
         if diag is not None and n_proposals // thin > 0:
             n_kept = n_proposals // thin
@@ -312,6 +333,7 @@ def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Option
     args = (C.byref(desc.c), buffer.data_ptr(), buffer.shape[0], _ptr(idx), int(ptr), out.data_ptr(), _ptr(scratch), n,
             int(n_steps), hs, ns, len(step_sizes), cl, int(rng_mode), int(seed), int(offset), _ptr(noise_rows), _ptr(noise),
             n_noise, _ptr(energy_out), C.byref(new_ptr))
+    _bind_workspace(desc, buffer.device)
     with torch.cuda.device(buffer.device):
         if peer_ptrs is None:
             rc = _lib.load().ebm_pcd_langevin_burst_f32(*args, _stream(buffer.device))
@@ -351,6 +373,7 @@ def langevin_burst_host(desc: EnergyDescriptor, x_host: torch.Tensor, out_host: 
                         n_steps: int, step_size: float, noise_scale: float, rng_mode: int, seed: int, offset: int) -> None:
     """End-to-end entry: pinned host in -> burst -> pinned host out, synchronised on return."""
     assert not x_host.is_cuda and not out_host.is_cuda and scratch.is_cuda
+    _bind_workspace(desc, scratch.device)
     with torch.cuda.device(scratch.device):
         rc = _lib.load().ebm_langevin_burst_host_f32(
             C.byref(desc.c), x_host.data_ptr(), out_host.data_ptr(), scratch.data_ptr(), x_host.shape[0], int(n_steps),
