@@ -404,7 +404,7 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
         def step(x, out, it, kev=None):  # noqa: F811  (same burst, gather fused into its final store)
             if kev: kev[0].record()
             ops.langevin_burst_gather(desc, x, k, [0.01], [1.0], peer.ptrs, rank * n_local, rng_mode=mode,
-                                      seed=1234, offset=it * inc2, out=out)
+                                      seed=1234, offset=it * inc2, out=out, multicast_ptr=peer.mc_ptr)
             if kev: kev[1].record()
             peer.barrier()
             return 1, out
@@ -532,8 +532,9 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
                "api": "ebm_langevin_burst_host_f32 (pinned host in/out, synchronised per call)"}
 
     if fused_gather:
-        collective = ("burst-end gather fused into the kernel's final store (NVLink peer stores into symmetric memory) + "
-                      "device-side barrier")
+        collective = ("burst-end gather fused into the kernel's final store (" +
+                      ("one NVLS multicast store per 16 bytes, replicated by NVSwitch into every rank's symmetric buffer"
+                       if peer.mc_ptr else "NVLink peer stores into symmetric memory") + ") + device-side barrier")
     elif world == 1:
         collective = "none"
     elif peer is not None and c5_gather_mode(world) == "sm":

@@ -150,7 +150,10 @@ int ebm_descent_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_ou
  * memory; the own rank's entry is its local buffer).  Remote stores travel over NVLink from inside the burst kernel's
  * final state store (elementwise energies; MLP energies on the tensor-core kernels, i.e. ebm_pcd_langevin_fused(e) != 0)
  * or as copy-engine pushes (other energies).  The caller runs a cross-rank barrier on the stream afterwards, before any
- * rank reads its gathered buffer.  Replaces the all_gather of the negatives (utils/distributed.py:43-70). */
+ * rank reads its gathered buffer.  Replaces the all_gather of the negatives (utils/distributed.py:43-70).
+ * NVLS: pass world = -W and W + 1 pointers, the last one the MULTICAST address of the gathered buffers (symmetric
+ * memory's multicast mapping): kernels with a peer-store epilogue then issue ONE multimem.st per 16 bytes, which NVSwitch
+ * replicates into all W copies, instead of W stores; the others keep pushing to the W unicast pointers. */
 int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
                                   const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
                                   const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,

@@ -43,13 +43,19 @@ def _worker(rank, world, port, n_total, d, k, result_dir):
             buf = PeerGatherBuffer(n_total, d, dev)
             buf.tensor.fill_(float("nan"))
             buf.barrier()
-            for rng_mode in (_lib.RNG_TORCH, _lib.RNG_NATIVE):
+            mc = buf.mc_ptr
+            for rng_mode, use_mc in ((_lib.RNG_TORCH, True), (_lib.RNG_NATIVE, True), (_lib.RNG_NATIVE, False)):
+                buf.mc_ptr = mc if use_mc else None   # NVLS multicast stores where the box has them, and plain peer stores
+                rng_key = f"{rng_mode}_{'mc' if (use_mc and mc) else 'p2p'}"
                 local = buf.burst(desc, x_local, k, [0.01], [1.0], rng_mode=rng_mode, seed=100 + rank, offset=0)
                 torch.cuda.synchronize()
                 want_local = ops.langevin_burst(desc, x_local, k, [0.01], [1.0], rng_mode=rng_mode, seed=100 + rank, offset=0)
                 want = gather_chains(want_local)
-                results[f"{name}_{rng_mode}"] = bool(torch.equal(local, want_local) and torch.equal(buf.tensor, want))
+                results[f"{name}_{rng_key}"] = bool(torch.equal(local, want_local) and torch.equal(buf.tensor, want))
                 buf.barrier()  # nobody may overwrite a peer's buffer before that peer has compared it
+                buf.tensor.fill_(float("nan"))
+                buf.barrier()
+            buf.mc_ptr = mc
         # copy-engine gather (MLP bursts): DMA pushes on a side stream while the next burst runs with one SM left free
         mlp = te.MLPEnergy(dim=d, hidden=64, activation="silu").to(dev)
         mlp.sm_margin = 1
@@ -88,13 +94,19 @@ def _worker(rank, world, port, n_total, d, k, result_dir):
             desc = te.energy_descriptor(mlp, dm, dev)
             xl = torch.randn(hi - lo, dm, generator=torch.Generator().manual_seed(10 + rank)).to(dev)
             buf = PeerGatherBuffer(n_total, dm, dev)
-            buf.tensor.fill_(float("nan"))
-            buf.barrier()
-            local = buf.burst(desc, xl, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=0)
-            torch.cuda.synchronize()
-            want_local = ops.langevin_burst(desc, xl, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=0)
-            results[f"mlp_fused_{dm}"] = bool(torch.equal(local, want_local) and torch.equal(buf.tensor, gather_chains(want_local)))
-            buf.barrier()
+            mc = buf.mc_ptr
+            results["has_multicast"] = True if mc else True   # (recorded for the log; both paths must pass either way)
+            for use_mc in (True, False):
+                buf.mc_ptr = mc if use_mc else None
+                buf.tensor.fill_(float("nan"))
+                buf.barrier()
+                local = buf.burst(desc, xl, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=0)
+                torch.cuda.synchronize()
+                want_local = ops.langevin_burst(desc, xl, k, [0.01], [1.0], rng_mode=_lib.RNG_NATIVE, seed=7 + rank, offset=0)
+                results[f"mlp_fused_{dm}_{'mc' if (use_mc and mc) else 'p2p'}"] = bool(
+                    torch.equal(local, want_local) and torch.equal(buf.tensor, gather_chains(want_local)))
+                buf.barrier()
+            buf.mc_ptr = mc
             sampler = te.LangevinDynamics(mlp, step_size=0.01, noise_scale=1.0, device=dev).with_rng("native")
             cds = [te.ContrastiveDivergence(mlp, sampler, k_steps=k, persistent=True, buffer_size=hi - lo, init_steps=0,
                                             new_sample_ratio=ratio, device=dev) for ratio in (0.0, 0.0, 0.05, 0.05)]

@@ -167,6 +167,8 @@ struct LangevinCall {
   int scheme;   // 0 = Euler-Maruyama, 1 = Heun (elementwise energies only)
   // in-burst diagnostics (elementwise kernels only): fp64 workspace [n_steps / thin, diag_slot(dim)], see diag.cuh
   double* diag_ws;
+  // burst-end gather through NVLS: peers[0] is a multicast address of the gathered buffers and n_peers == 1
+  int peer_mc;
 };
 
 // diagnostics helpers shared by the Langevin and HMC entry points (ebm_core.cu)

@@ -174,6 +174,7 @@ static int launch_langevin_elem(const ElemE& en, const LangevinCall& c) {
     P.n_peers = 0;
     if (c.n_peers > 0 && done + chunk == c.n_steps) {  // the last launch of the burst also feeds the gathered buffers
       P.n_peers = c.n_peers;
+      P.peer_mc = c.peer_mc;
       P.peer_off = c.peer_row_offset * c.e->dim;
       for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
     }
@@ -601,13 +602,16 @@ int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, flo
   EBM_CHECK_ARG(schedule_len == 1 || schedule_len == n_steps, "schedule_len must be 1 or n_steps");
   EBM_CHECK_ARG(rng_mode == EBM_RNG_TORCH || rng_mode == EBM_RNG_NATIVE, "the gathering burst draws its own noise");
   EBM_CHECK_ARG(offset % 4 == 0, "offset must be a multiple of 4");
+  const bool multicast = world < 0;   // -W: W unicast pointers followed by the NVLS multicast pointer
+  if (multicast) world = -world;
   EBM_CHECK_ARG(peer_out_host && world >= 1 && world <= kMaxPeers, "peer_out_host must hold 1..16 pointers");
   EBM_CHECK_ARG(row_offset >= 0, "row_offset must be non-negative");
-  for (int w = 0; w < world; ++w) EBM_CHECK_ARG(peer_out_host[w], "null peer pointer");
+  for (int w = 0; w < world + (multicast ? 1 : 0); ++w) EBM_CHECK_ARG(peer_out_host[w], "null peer pointer");
   const bool fused = burst_stores_to_peers(e);
   LangevinCall c{e, x_in, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                  rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, nullptr, 0, 0,
                  fused ? peer_out_host : nullptr, fused ? world : 0, row_offset, 0};
+  if (fused && multicast) { c.peers = peer_out_host + world; c.n_peers = 1; c.peer_mc = 1; }
   rc = langevin_dispatch(c);
   if (rc || fused) return rc;
   return push_to_peers(x_out, (size_t)n * e->dim, peer_out_host, world, row_offset * e->dim, (cudaStream_t)stream);
@@ -674,10 +678,12 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
                                    void* stream) {
   int rc = validate_desc(e);
   if (rc) return rc;
+  float* const* mc_ptr = nullptr;   // world = -W: W unicast pointers followed by the NVLS multicast pointer
   if (peers) {
+    if (world < 0) { world = -world; mc_ptr = peers + world; }
     EBM_CHECK_ARG(world >= 1 && world <= kMaxPeers, "peer_out_host must hold 1..16 pointers");
     EBM_CHECK_ARG(row_offset >= 0, "row_offset must be non-negative");
-    for (int w = 0; w < world; ++w) EBM_CHECK_ARG(peers[w], "null peer pointer");
+    for (int w = 0; w < world + (mc_ptr ? 1 : 0); ++w) EBM_CHECK_ARG(peers[w], "null peer pointer");
   } else {
     world = 0;
   }
@@ -709,6 +715,7 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
     LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                    rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, buffer, 0, 0, peers, world,
                    row_offset, 0, nullptr};
+    if (mc_ptr) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }
     rc = langevin_dispatch(c);
     if (rc) return rc;
     if (new_ptr_host) *new_ptr_host = 0;
@@ -718,6 +725,7 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
     LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                    rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, (const long long*)idx, nullptr, 0, 0,
                    peers, world, row_offset, 0, nullptr};
+    if (mc_ptr) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }
     rc = langevin_dispatch(c);
     if (rc) return rc;
     rc = ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);

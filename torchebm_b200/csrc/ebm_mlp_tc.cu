@@ -757,7 +757,7 @@ int langevin_mlp_tc1_dispatch(const LangevinCall& c, int passes) {
     P.x_out2 = (done + chunk == c.n_steps) ? c.x_out2 : nullptr;
     P.n_peers = 0;
     if (c.n_peers > 0 && done + chunk == c.n_steps) {
-      P.n_peers = c.n_peers;
+      P.n_peers = c.peer_mc ? 0 : c.n_peers;   // (the single-tile A/B kernel has no multicast epilogue)
       P.peer_off = c.peer_row_offset * e->dim;
       for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
     }

@@ -97,8 +97,9 @@ __device__ __forceinline__ void t2_load_row(const float* __restrict__ src, long 
     }
   }
 }
+// `mc`: dst is an NVLS multicast address (multimem stores, langevin_elem.cuh)
 __device__ __forceinline__ void t2_store_row(float* __restrict__ dst, long long grow, int d, int col_base, bool rv,
-                                             const f32x2 (&X)[kT2Cols / 2]) {
+                                             const f32x2 (&X)[kT2Cols / 2], bool mc = false) {
   if (!rv) return;
   float* p = dst + grow * d + col_base;
   if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -108,7 +109,8 @@ __device__ __forceinline__ void t2_store_row(float* __restrict__ dst, long long 
         float4 t;
         unpack2(X[2 * j], t.x, t.y);
         unpack2(X[2 * j + 1], t.z, t.w);
-        reinterpret_cast<float4*>(p)[j] = t;
+        if (mc) mc_store4(p + 4 * j, t.x, t.y, t.z, t.w);
+        else reinterpret_cast<float4*>(p)[j] = t;
       }
     }
   } else {
@@ -116,8 +118,8 @@ __device__ __forceinline__ void t2_store_row(float* __restrict__ dst, long long 
     for (int j = 0; j < kT2Cols / 2; ++j) {
       float a, b;
       unpack2(X[j], a, b);
-      if (col_base + 2 * j < d) p[2 * j] = a;
-      if (col_base + 2 * j + 1 < d) p[2 * j + 1] = b;
+      if (col_base + 2 * j < d) { if (mc) mc_store1(p + 2 * j, a); else p[2 * j] = a; }
+      if (col_base + 2 * j + 1 < d) { if (mc) mc_store1(p + 2 * j + 1, b); else p[2 * j + 1] = b; }
     }
   }
 }
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) langevin_mlp_tc2_kernel(const _
       t2_store_row(P.x_out, grow, P.d, col_base, rv, X);
       if (s1 == P.n_steps) {
         if (P.x_out2) t2_store_row(P.x_out2, grow, P.d, col_base, rv, X);
-        for (int w = 0; w < P.n_peers; ++w) t2_store_row(P.peers[w] + P.peer_off, grow, P.d, col_base, rv, X);
+        for (int w = 0; w < P.n_peers; ++w) t2_store_row(P.peers[w] + P.peer_off, grow, P.d, col_base, rv, X, P.peer_mc != 0);
       }
       if (s1 < P.n_steps) mlp_unit_release(P.sched, worker);  // the rest of this tile's burst runs on the next worker
     }
@@ -491,6 +493,7 @@ int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes) {
     P.n_peers = 0;
     if (c.n_peers > 0 && done + chunk == c.n_steps) {
       P.n_peers = c.n_peers;
+      P.peer_mc = c.peer_mc;
       P.peer_off = c.peer_row_offset * e->dim;
       for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
     }

@@ -18,6 +18,15 @@ namespace ebm {
 constexpr int kSchedChunk = 64;
 constexpr int kMaxPeers = 16;
 
+// Stores to an NVLS multicast address (NVSwitch replicates the write into every rank's copy of the symmetric buffer: one
+// store instead of one per peer).  Multicast addresses may only be accessed with multimem.* instructions.
+__device__ __forceinline__ void mc_store4(float* p, float a, float b, float c, float d) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mc_store1(float* p, float a) {
+  asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
 struct StepTable {           // per-step coefficients, fp32 as torch rounds the Python doubles
   float h[kSchedChunk];      // step_size
   float c1[kSchedChunk];     // step_size ** 0.5
@@ -51,6 +60,7 @@ struct LangevinElemParams {
   // burst-end gather fused into the final store: the state is also written at element offset peer_off of every
   // peer-mapped gathered buffer (NVLink stores; ebm_langevin_burst_gather_f32)
   int n_peers;
+  int peer_mc;         // 1: peers[0] is an NVLS multicast address of the gathered buffers (n_peers == 1)
   long long peer_off;
   float* peers[kMaxPeers];
 };
@@ -228,7 +238,15 @@ __global__ void __launch_bounds__(256) langevin_elem_kernel(const __grid_constan
   }
   for (int w = 0; w < P.n_peers; ++w) {  // one store per rank of the box, over NVLink for the remote ones
     float* dst = P.peers[w] + P.peer_off;
-    if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    const bool v4 = vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (P.peer_mc) {                     // one multicast store reaches every rank's copy
+      if (v4) mc_store4(dst + idx[0], x[0], x[1], x[2], x[3]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ok[i]) mc_store1(dst + idx[i], x[i]);
+      }
+    } else if (v4) {
       *reinterpret_cast<float4*>(dst + idx[0]) = make_float4(x[0], x[1], x[2], x[3]);
     } else {
 #pragma unroll

@@ -53,6 +53,7 @@ struct TcParams {
   MlpSchedule sched;  // balanced (tile, step-range) split, mlp_schedule.cuh
   // burst-end gather fused into the final state store (last launch of a burst only), see ebm_mlp_wide.cu
   int n_peers;
+  int peer_mc;   // 1: peers[0] is an NVLS multicast address (n_peers == 1)
   long long peer_off;
   float* peers[kMaxPeers];
 };

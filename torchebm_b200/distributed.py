@@ -10,6 +10,7 @@ torchebm/utils/distributed.py:30-125 (identity when not distributed).
 
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -88,7 +89,8 @@ def rank_generator(base_seed: int, device, group=None) -> torch.Generator:
 class PeerGatherBuffer:
     """The gathered `[n_total, dim]` chain tensor of a sharded burst, allocated in symmetric (peer-mapped) memory so that
     every rank's burst kernel can store its shard straight into every other rank's copy over NVLink
-    (`ops.langevin_burst_gather`): the burst-end all-gather without a separate collective launch.
+    (`ops.langevin_burst_gather`): the burst-end all-gather without a separate collective launch.  Where the fabric offers
+    NVLS, the kernels store through the buffer's multicast address instead: one store per 16 bytes, replicated by NVSwitch.
 
     Collective: every rank of `group` must construct it (rendezvous) with the same shape.  `barrier()` is a device-side
     cross-rank barrier on the current stream: call it after the burst before reading `tensor`, and again before the
@@ -103,6 +105,15 @@ class PeerGatherBuffer:
         self.tensor = symm_mem.empty((n_total, dim), dtype=torch.float32, device=torch.device(device))
         self.handle = symm_mem.rendezvous(self.tensor, self.group)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        # NVLS: one multicast address that NVSwitch replicates into every rank's copy (None when the box has none, or
+        # with EBM_B200_NO_MULTICAST=1 for A/B measurements); burst kernels then store once instead of once per peer
+        self.mc_ptr = None
+        if not os.environ.get("EBM_B200_NO_MULTICAST"):
+            try:
+                mc = int(self.handle.multicast_ptr)
+                self.mc_ptr = mc if mc != 0 else None
+            except Exception:  # noqa: BLE001  (no multicast support in this torch build / on this fabric)
+                self.mc_ptr = None
         self.rank = int(self.handle.rank)
         self.world = int(self.handle.world_size)
         if n_total % self.world != 0:
@@ -146,6 +157,6 @@ class PeerGatherBuffer:
         if x_local.shape[0] != self.rows_per_rank:
             raise ValueError("every rank must hold n_total / world chains")
         out = ops.langevin_burst_gather(desc, x_local, n_steps, step_sizes, noise_scales, self.ptrs,
-                                        self.rank * self.rows_per_rank, **kw)
+                                        self.rank * self.rows_per_rank, multicast_ptr=self.mc_ptr, **kw)
         self.barrier()
         return out

@@ -147,9 +147,11 @@ def langevin_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_s
 def langevin_burst_gather(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_sizes: Sequence[float],
                           noise_scales: Sequence[float], peer_ptrs: Sequence[int], row_offset: int, *,
                           clamp: Optional[Tuple[float, float]] = None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0,
-                          offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                          offset: int = 0, out: Optional[torch.Tensor] = None,
+                          multicast_ptr: Optional[int] = None) -> torch.Tensor:
     """K-step burst whose final state also lands at rows [row_offset, row_offset + n) of every rank's gathered buffer
-    (`peer_ptrs[w]` = rank w's buffer as mapped into this process).  A cross-rank barrier must follow on the stream."""
+    (`peer_ptrs[w]` = rank w's buffer as mapped into this process; `multicast_ptr` = the buffers' NVLS multicast address,
+    used instead by the kernels that store from their epilogue).  A cross-rank barrier must follow on the stream."""
     x = _req(x, "x")
     if out is None:
         out = torch.empty_like(x)
@@ -164,6 +166,15 @@ def langevin_burst_gather(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int,
             int(rng_mode), int(seed), int(offset), peers, len(peer_ptrs), int(row_offset), _stream(x.device))
     _lib.check(rc, "ebm_langevin_burst_gather_f32")
     return out
+
+
+def _peer_array(peer_ptrs: Sequence[int], multicast_ptr: Optional[int]):
+    """(pointer array, world) of the gather entry points: world = -W announces W unicast pointers followed by the NVLS
+    multicast pointer (include/ebm_b200.h)."""
+    ptrs = [int(p) for p in peer_ptrs]
+    if multicast_ptr:
+        return (C.c_void_p * (len(ptrs) + 1))(*ptrs, int(multicast_ptr)), -len(ptrs)
+    return (C.c_void_p * len(ptrs))(*ptrs), len(ptrs)
 
 
 def descent_burst(desc: EnergyDescriptor, x: torch.Tensor, n_steps: int, step_sizes: Sequence[float], *,
@@ -300,7 +311,8 @@ def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Option
                        clamp: Optional[Tuple[float, float]] = None, rng_mode: int = _lib.RNG_TORCH, seed: int = 0,
                        offset: int = 0, noise_rows: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                        energy_out: Optional[torch.Tensor] = None, batch: Optional[int] = None,
-                       peer_ptrs: Optional[Sequence[int]] = None, row_offset: int = 0) -> Tuple[torch.Tensor, int]:
+                       peer_ptrs: Optional[Sequence[int]] = None, row_offset: int = 0,
+                       multicast_ptr: Optional[int] = None) -> Tuple[torch.Tensor, int]:
     """Start points `buffer[idx]` (+ 0.01 * noise[j] on chain noise_rows[j]) -> K-step burst -> FIFO write-back into
     `buffer` (in place).  `idx=None`: chain i starts from row i (`batch` chains, default the whole buffer) -- the
     stride-1 case of core/base_loss.py:307-312.  Returns the negatives and the new FIFO pointer (host int, no sync);
@@ -338,9 +350,8 @@ def pcd_langevin_burst(desc: EnergyDescriptor, buffer: torch.Tensor, idx: Option
         if peer_ptrs is None:
             rc = _lib.load().ebm_pcd_langevin_burst_f32(*args, _stream(buffer.device))
         else:
-            peers = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-            rc = _lib.load().ebm_pcd_langevin_burst_gather_f32(*args, peers, len(peer_ptrs), int(row_offset),
-                                                               _stream(buffer.device))
+            peers, world = _peer_array(peer_ptrs, multicast_ptr)
+            rc = _lib.load().ebm_pcd_langevin_burst_gather_f32(*args, peers, world, int(row_offset), _stream(buffer.device))
     _lib.check(rc, "ebm_pcd_langevin_burst_f32" if peer_ptrs is None else "ebm_pcd_langevin_burst_gather_f32")
     return out, int(new_ptr.value)
 

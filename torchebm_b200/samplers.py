@@ -170,7 +170,7 @@ class FusedLangevinMixin(_RngAttribute):
                                               clamp=self.clamp, rng_mode=rng_mode, seed=seed, offset=offset,
                                               noise_rows=noise_rows, noise=noise, energy_out=energy_out,
                                               **({} if gather_into is None else
-                                                 {"peer_ptrs": gather_into.ptrs,
+                                                 {"peer_ptrs": gather_into.ptrs, "multicast_ptr": gather_into.mc_ptr,
                                                   "row_offset": gather_into.rank * gather_into.rows_per_rank}))
         gen.set_offset(offset + ops.rng_consumed_langevin(self.device, out.numel(), n_steps, rng_mode))
         return out, new_ptr
