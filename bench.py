@@ -312,11 +312,12 @@ def make_workload(name: str, n_local: int, dev, rng: str = "torch"):
             torch.manual_seed(0)
             model, eps_h = te.MLPEnergy(dim=d, hidden=128, activation="silu").to(dev), 0.05
         desc = te.energy_descriptor(model, d, dev)
-        inc = ops.rng_consumed_hmc(dev, n_local, d, 1, _lib.RNG_TORCH)
+        hmode = _lib.RNG_TORCH if name == "c4" else mode   # C4 (a BASELINE config): always the reference-identical stream
+        inc = ops.rng_consumed_hmc(dev, n_local, d, 1, hmode)
 
         def step(x, out, it, kev=None):
             if kev: kev[0].record()
-            ops.hmc_burst(desc, x, 1, k, [eps_h], rng_mode=_lib.RNG_TORCH, seed=1234, offset=it * inc, out=out)
+            ops.hmc_burst(desc, x, 1, k, [eps_h], rng_mode=hmode, seed=1234, offset=it * inc, out=out)
             if kev: kev[1].record()
             return 1, out
 
@@ -362,6 +363,8 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
 
     dev = torch.device("cuda", local)
     desc_text, n_total, d, k = WORKLOADS[workload]
+    if workload in ("c1", "c4"):
+        rng = "torch"   # BASELINE configs on analytic energies always run the reference-identical stream
     if workload in WEAK:
         n_total *= world
     lo, hi = shard_bounds(n_total, rank, world)
@@ -534,7 +537,7 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
     if fused_gather:
         collective = ("burst-end gather fused into the kernel's final store (" +
                       ("one NVLS multicast store per 16 bytes, replicated by NVSwitch into every rank's symmetric buffer"
-                       if peer.mc_ptr else "NVLink peer stores into symmetric memory") + ") + device-side barrier")
+                       if (peer.mc_ptr and workload == "c5") else "NVLink peer stores into symmetric memory") + ") + device-side barrier")
     elif world == 1:
         collective = "none"
     elif peer is not None and c5_gather_mode(world) == "sm":
