@@ -54,7 +54,7 @@ WORKLOADS = {
     "mlp128_bf16": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (single-pass bf16)", 65536, 128, 100),
     "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
     "hmc_mlp128": ("HamiltonianMonteCarlo MLP 128-128-128-1 SiLU dim=128 n_chains=65536 L=10, 1 proposal per step, "
-                   "step_size=0.05 (fused fp32 HMC kernel)", 65536, 128, 10),
+                   "step_size=0.05 (tcgen05 kernel, bf16 hi/lo split operands)", 65536, 128, 10),
     "c3": ("ContrastiveDivergence persistent=True negatives: replay-buffer gather -> LangevinDynamics MLP 784-128-128-1 SiLU "
            "k=20 step_size=0.01 -> FIFO write-back; n_chains=65536=buffer_size", 65536, 784, 20),
     # C5 = C3 sharded over the GPUs of one box: 65 536 chains PER GPU (524 288 at 8 GPUs), weak scaling
