@@ -18,7 +18,15 @@
 // Warp roles: warp 0 = TMEM allocation + single-thread MMA issue, warp 1 = bulk-copy producer, warps 2-3 idle (they
 // complete the role warpgroup that gives its registers away), warps 4..19 = epilogue
 // (thread = one chain row x 32 hidden columns in the 128-wide phases, x 16 state columns per chunk in the E4 phase).
-// TMEM columns: [0,128) z1 / t, [128,256) z2, [256,384) act'(z1), [384,448) G even chunks, [448,512) G odd chunks.
+// Every A operand (h1, delta2, delta1, the updated state chunk) lives in TENSOR memory, written by the epilogue with
+// tcgen05.st as packed bf16 pairs (row = lane, column j = elements 2j, 2j+1) and read by tcgen05.mma's [a_tmem] form:
+// with both operands in shared memory a no-swizzle 128x128x16 product needs 107 cycles (shared-memory operand
+// bandwidth), with A in tensor memory 74 (tools/umma_probe.cu), and the epilogue's operand stores, proxy fences and
+// the 128 KB of operand buffers disappear from shared memory, which goes to a deeper weight ring instead.
+// TMEM columns: [0,128)   z1 -> act'(z1) in place -> z1 of the next step (accumulated chunk by chunk in E4)
+//               [128,256) z2 -> G even chunks [128,192), G odd chunks [192,256)
+//               [256,384) A operand of the 128-wide products: hi [256,320), lo [320,384)
+//               [384,512) t = delta2 . W2 (read by E3) -> state-chunk operand buffers b = 0, 1: hi [384+64b, +32), lo [+32, +64)
 #include "mlp_tc_common.cuh"   // packed fp32x2 epilogue arithmetic, bf16 hi/lo split, TMEM <-> register pairs
 
 namespace ebm {
@@ -30,7 +38,7 @@ constexpr int kWdH = 128;               // padded hidden width
 constexpr int kWdChunk = 64;            // state columns per W1 ring item
 constexpr int kWdStageBytes = 32768;    // ring item: W1 chunk hi (16 KB) + lo (16 KB), or W2 hi, or W2 lo
 constexpr int kWdHalf = 16384;
-constexpr int kWdStages = 3;
+constexpr int kWdStages = 6;
 constexpr int kWdEpiWarps = 16;
 constexpr int kWdRoleWarps = 4;         // one warpgroup: MMA issue, bulk-copy producer, two idle warps (setmaxnreg works per warpgroup)
 constexpr int kWdThreads = 32 * (kWdRoleWarps + kWdEpiWarps);
@@ -43,11 +51,7 @@ constexpr int kWdMaxDim = 4096;
 
 struct WdSmem {
   static constexpr int ring = 0;
-  static constexpr int a_hi = ring + kWdStages * kWdStageBytes;  // [128 x 128] bf16: h1 / delta2 / delta1
-  static constexpr int a_lo = a_hi + kWdM * kWdH * 2;
-  static constexpr int xa = a_lo + kWdM * kWdH * 2;              // 2 buffers x ([128 x 64] bf16 hi, lo): state chunk, A of GEMM1
-  static constexpr int xa_buf = 2 * kWdM * kWdChunk * 2;         // bytes per buffer (hi then lo)
-  static constexpr int b1 = xa + 2 * xa_buf;
+  static constexpr int b1 = ring + kWdStages * kWdStageBytes;
   static constexpr int b2 = b1 + kWdH * 4;
   static constexpr int w3 = b2 + kWdH * 4;
   static constexpr int bars = w3 + kWdH * 4;
@@ -66,6 +70,9 @@ struct WdSmem {
   static constexpr int total = push_cnt + 16;
 };
 static_assert(WdSmem::total <= 232448, "shared memory budget of one sm_100 CTA exceeded");
+
+// tensor-memory column map (see the header comment)
+constexpr uint32_t kWdTmZ1 = 0, kWdTmZ2 = 128, kWdTmG = 128, kWdTmA = 256, kWdTmALo = 320, kWdTmT = 384, kWdTmXa = 384;
 
 struct WdParams {
   const uint8_t* ws;  // workspace: NC W1 chunk blobs, W2 hi blob, W2 lo blob (mlp_wide_prep_kernel)
@@ -92,6 +99,21 @@ struct WdParams {
   long long peer_off;
   float* peers[kMaxPeers];
 };
+
+// Timeline tracing of CTA 0 (tuning builds only: python -m torchebm_b200.build --variant trace EBM_WD_TRACE; read with
+// tools/wd_trace.py).  One record = (clock64 << 16) | tag, written by the single thread that owns a role.
+#ifdef EBM_WD_TRACE
+constexpr int kWdTraceLen = 8192;
+__device__ unsigned long long g_wd_trace[4 * kWdTraceLen];
+#define WD_TR_DECL(cond) const bool tr_on = (blockIdx.x == 0) && (cond); int tr_i = 0
+#define WD_TR(role, tag)                                                                                            \
+  do {                                                                                                              \
+    if (tr_on && tr_i < kWdTraceLen) g_wd_trace[(role) * kWdTraceLen + tr_i++] = ((unsigned long long)clock64() << 16) | (unsigned)(tag); \
+  } while (0)
+#else
+#define WD_TR_DECL(cond)
+#define WD_TR(role, tag) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t wd_bar(uint8_t* smem, int idx) { return smem_u32(smem + WdSmem::bars + idx * 8); }
 
@@ -149,43 +171,35 @@ __global__ void mlp_wide_prep_kernel(const float* __restrict__ W1, const float* 
 }
 
 // ---- epilogue helpers -----------------------------------------------------------------------------------
-// 16 consecutive columns [col0, col0+16) of row r -> hi and lo copies of a [128 x C] core-matrix operand
-__device__ __forceinline__ void wd_store16(uint8_t* hi_base, uint8_t* lo_base, int r, int col0, const float* v, bool with_lo) {
+// 4 packed bf16x2 words = 8 consecutive K elements of this thread's row -> 4 tensor-memory columns
+__device__ __forceinline__ void tmem_st4_raw(uint32_t taddr, const uint32_t (&w)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3])
+               : "memory");
+}
+// 16 consecutive operand columns (8 packed pairs) of this thread's row: hi words to t_hi, residual words to t_lo
+// (four 4-column stores: splitting all 8 pairs first costs 16 live registers the update phase does not have)
+__device__ __forceinline__ void wd_put16p(uint32_t t_hi, uint32_t t_lo, const f32x2* v, bool with_lo) {
 #pragma unroll
-  for (int oct = 0; oct < 2; ++oct) {
+  for (int o = 0; o < 2; ++o) {
     uint32_t ph[4], pl[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = v[oct * 8 + 2 * j], b = v[oct * 8 + 2 * j + 1];
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
-      ph[j] = hu;
-      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
-      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
-    }
-    const int off = core_offset(r, col0 + oct * 8, kWdM);
-    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    if (with_lo) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    for (int j = 0; j < 4; ++j) split2(v[4 * o + j], ph[j], pl[j], with_lo);
+    tmem_st4_raw(t_hi + 4 * o, ph);
+    if (with_lo) tmem_st4_raw(t_lo + 4 * o, pl);
   }
 }
-
-// packed form: 8 pairs = 16 consecutive columns (split2: truncated hi, rounded residual)
-__device__ __forceinline__ void wd_store16p(uint8_t* hi_base, uint8_t* lo_base, int r, int col0, const f32x2* v, bool with_lo) {
+__device__ __forceinline__ void wd_put16(uint32_t t_hi, uint32_t t_lo, const float* v, bool with_lo) {
+  f32x2 p[8];
 #pragma unroll
-  for (int oct = 0; oct < 2; ++oct) {
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split2(v[oct * 4 + j], ph[j], pl[j], with_lo);
-    const int off = core_offset(r, col0 + oct * 8, kWdM);
-    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    if (with_lo) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-  }
+  for (int j = 0; j < 8; ++j) p[j] = pack2(v[2 * j], v[2 * j + 1]);
+  wd_put16p(t_hi, t_lo, p, with_lo);
 }
 
-// make this warp's generic-proxy shared-memory writes visible to the tensor core, then one arrival per warp
+// this warp's tensor-memory operand stores have landed -> one arrival per warp for the MMA warp
 __device__ __forceinline__ void wd_publish(uint32_t bar) {
+  tmem_st_wait();
   tcgen05_fence_before();
-  fence_proxy_async();
   __syncwarp();
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 st;\n\t"
@@ -266,20 +280,27 @@ __device__ __forceinline__ void wd_store_x16(float* __restrict__ dst, long long 
 }
 
 // ---- MMA issue helpers (converged warp, one elected lane issues) -----------------------------------------------------------------------
-// `ksteps` k-steps of 16; descriptors advance by (a_step, b_step) bytes per k-step; three passes for split operands
-__device__ __forceinline__ void wd_mma_block(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b_hi,
-                                             uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
-                                             int k_begin, int k_end, int passes, bool accumulate_first, bool leader) {
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// `ksteps` k-steps of 16; the A operand advances by 8 tensor-memory columns per k-step, the B descriptor by b_step bytes;
+// three passes for split operands
+__device__ __forceinline__ void wd_mma_block(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                             uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int k_begin,
+                                             int k_end, int passes, bool accumulate_first, bool leader) {
   if (!leader) return;   // (the warp runs converged; one elected lane issues, see umma.cuh: elect_one)
   for (int kk = k_begin; kk < k_end; ++kk) {
-    const uint64_t ah = make_smem_desc(a_hi + kk * a_step, kWdM * 16, 128);
     const uint64_t bh = make_smem_desc(b_hi + kk * b_step, b_lbo, b_sbo);
-    mma_bf16(tmem_d, ah, bh, idesc, accumulate_first || kk > k_begin);
+    mma_bf16_ts(tmem_d, a_hi + 8 * kk, bh, idesc, accumulate_first || kk > k_begin);
     if (passes == 3) {
-      const uint64_t al = make_smem_desc(a_lo + kk * a_step, kWdM * 16, 128);
       const uint64_t bl = make_smem_desc(b_lo + kk * b_step, b_lbo, b_sbo);
-      mma_bf16(tmem_d, al, bh, idesc, true);
-      mma_bf16(tmem_d, ah, bl, idesc, true);
+      mma_bf16_ts(tmem_d, a_lo + 8 * kk, bh, idesc, true);
+      mma_bf16_ts(tmem_d, a_hi + 8 * kk, bl, idesc, true);
     }
   }
 }
@@ -335,6 +356,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
   if (warp == 1) {
     // ---- producer: stream the weight blobs through the ring in the fixed item order --------------------------
     if (lane == 0) {
+      WD_TR_DECL(true);
       uint32_t it = 0;
       const uint8_t* w2hi = P.ws + (size_t)NC * kWdStageBytes;
       const uint8_t* w2lo = w2hi + kWdStageBytes;
@@ -342,6 +364,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const int s = it % kWdStages;
         mbar_wait(wd_bar(smem, WdSmem::ring_empty + s), ((it / kWdStages) & 1) ^ 1);
         const uint32_t full = wd_bar(smem, WdSmem::ring_full + s);
+        WD_TR(3, 256 + (it & 255));
         mbar_expect_tx(full, kWdStageBytes);
         bulk_g2s(smem_u32(smem + WdSmem::ring + s * kWdStageBytes), src, kWdStageBytes, full);
         ++it;
@@ -360,8 +383,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     // ---- MMA issue ----------------------------------------------------------------------------------------------
     {
       const bool leader = elect_one();
-      const uint32_t a_hi = smem_u32(smem + WdSmem::a_hi), a_lo = smem_u32(smem + WdSmem::a_lo);
-      const uint32_t xa = smem_u32(smem + WdSmem::xa);
+      WD_TR_DECL(leader);
+      const uint32_t a_hi = tmem + kWdTmA, a_lo = tmem + kWdTmALo;
       const uint32_t ring = smem_u32(smem + WdSmem::ring);
       const uint32_t idesc_fwd = make_idesc_bf16(kWdM, kWdH, false);
       const uint32_t idesc_bwd = make_idesc_bf16(kWdM, kWdH, true);
@@ -375,9 +398,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       auto gemm1_chunk = [&](uint32_t item, int c) {
         const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
         const uint32_t w = stage_addr(item);
-        const uint32_t xa_hi = xa + (xcnt & 1) * WdSmem::xa_buf;
-        wd_mma_block(tmem + 0, xa_hi, xa_hi + WdSmem::xa_buf / 2, 2 * core_col, w, w + kWdHalf, 2 * core_col, core_col, 128,
-                     idesc_fwd, 0, (valid + 15) / 16, P.passes, c > 0, leader);
+        const uint32_t xa_hi = tmem + kWdTmXa + 64 * (xcnt & 1);
+        wd_mma_block(tmem + kWdTmZ1, xa_hi, xa_hi + 32, w, w + kWdHalf, 2 * core_col, core_col, 128, idesc_fwd, 0,
+                     (valid + 15) / 16, P.passes, c > 0, leader);
       };
       auto xa_wait = [&]() {
         mbar_wait(wd_bar(smem, WdSmem::xa_full + (xcnt & 1)), (xcnt >> 1) & 1);
@@ -389,7 +412,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const int valid = (P.d - c * kWdChunk) < kWdChunk ? (P.d - c * kWdChunk) : kWdChunk;
         const int ncols = ((valid + 15) / 16) * 16;
         const uint32_t w = stage_addr(item);
-        wd_mma_block(tmem + 384 + 64 * (c & 1), a_hi, a_lo, 2 * core_col, w, w + kWdHalf, 256, 128, core_col,
+        wd_mma_block(tmem + kWdTmG + 64 * (c & 1), a_hi, a_lo, w, w + kWdHalf, 256, 128, core_col,
                      make_idesc_bf16(kWdM, ncols, true), 0, k_h1, P.passes, false, leader);
         if (leader) mma_commit(wd_bar(smem, WdSmem::g_full + (c & 1)));
       };
@@ -399,10 +422,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
           tcgen05_fence_after();
           if (backward)
-            wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 256, 128, core_col, idesc_bwd, kk, kk + 1, P.passes, kk > 0, leader);
+            wd_mma_block(tmem_d, a_hi, a_lo, w_hi, w_lo, 256, 128, core_col, idesc_bwd, kk, kk + 1, P.passes, kk > 0, leader);
           else
-            wd_mma_block(tmem_d, a_hi, a_lo, 2 * core_col, w_hi, w_lo, 2 * core_col, core_col, 128, idesc_fwd, kk, kk + 1,
-                         P.passes, kk > 0, leader);
+            wd_mma_block(tmem_d, a_hi, a_lo, w_hi, w_lo, 2 * core_col, core_col, 128, idesc_fwd, kk, kk + 1, P.passes, kk > 0,
+                         leader);
         }
         // chunks beyond ksteps are still published by the epilogue: consume their phases
         for (int kk = ksteps; kk < 8; ++kk) mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
@@ -422,13 +445,17 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
         for (int k = 0; k < n_unit_steps; ++k) {
           const bool last = (k == n_unit_steps - 1);
+          WD_TR(0, 1 * 256);
           ring_wait(it);
           ring_wait(it + 1);
+          WD_TR(0, 2 * 256);
           const uint32_t w2hi = stage_addr(it), w2lo = stage_addr(it + 1);
-          gemm_chunked(tmem + 128, w2hi, w2lo, false, k_h1);   // z2 = h1 . W2^T
+          gemm_chunked(tmem + kWdTmZ2, w2hi, w2lo, false, k_h1);   // z2 = h1 . W2^T
           if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
-          gemm_chunked(tmem + 0, w2hi, w2lo, true, k_h2);      // t = delta2 . W2
+          WD_TR(0, 3 * 256);
+          gemm_chunked(tmem + kWdTmT, w2hi, w2lo, true, k_h2);    // t = delta2 . W2
           if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
+          WD_TR(0, 4 * 256);
           ring_release(it);
           ring_release(it + 1);
           it += 2;
@@ -436,15 +463,19 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           for (int kk = 0; kk < 8; ++kk) mbar_wait(wd_bar(smem, WdSmem::a_chunk + kk), a_par);
           a_par ^= 1;
           tcgen05_fence_after();
+          WD_TR(0, 5 * 256);
           ring_wait(it);
+          WD_TR(0, 6 * 256);
           gemm4_chunk(it, 0);
           if (NC > 1) { ring_wait(it + 1); gemm4_chunk(it + 1, 1); }
           for (int c = 0; c < NC; ++c) {
             xa_wait();                                                       // x'_c published, G[c & 1] drained
+            WD_TR(0, 7 * 256 + c);
             if (!last) gemm1_chunk(it + c, c);
             xa_release();
             ring_release(it + c);
-            if (c + 2 < NC) { ring_wait(it + c + 2); gemm4_chunk(it + c + 2, c + 2); }
+            WD_TR(0, 9 * 256 + c);
+            if (c + 2 < NC) { ring_wait(it + c + 2); WD_TR(0, 8 * 256 + c); gemm4_chunk(it + c + 2, c + 2); WD_TR(0, 10 * 256 + c); }
           }
           it += NC;
           if (!last) if (leader) mma_commit(wd_bar(smem, WdSmem::acc_full));
@@ -523,9 +554,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     const f32x2* b1 = reinterpret_cast<const f32x2*>(reinterpret_cast<const float*>(smem + WdSmem::b1) + hcol);
     const f32x2* b2 = reinterpret_cast<const f32x2*>(reinterpret_cast<const float*>(smem + WdSmem::b2) + hcol);
     const f32x2* w3 = reinterpret_cast<const f32x2*>(reinterpret_cast<const float*>(smem + WdSmem::w3) + hcol);
-    uint8_t* const a_hi = smem + WdSmem::a_hi;
-    uint8_t* const a_lo = smem + WdSmem::a_lo;
-    uint8_t* const xa = smem + WdSmem::xa;
+    const uint32_t a_hi = lane_addr + kWdTmA + hcol / 2, a_lo = lane_addr + kWdTmALo + hcol / 2;   // this thread's operand columns
     const uint32_t acc_bar = wd_bar(smem, WdSmem::acc_full);
     const uint32_t xa_full = wd_bar(smem, WdSmem::xa_full), xa_empty = wd_bar(smem, WdSmem::xa_empty);
     uint32_t xcnt = 0;  // running count of published state chunks: buffer xcnt & 1, use (xcnt >> 1) of that buffer
@@ -534,6 +563,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     const uintptr_t ptr_bits = (uintptr_t)P.x_in | (uintptr_t)P.x_out | (uintptr_t)P.traj | (uintptr_t)P.x_out2;
     const int vec = (P.d % 8 == 0 && (ptr_bits & 31) == 0) ? 2 : ((P.d % 4 == 0 && (ptr_bits & 15) == 0) ? 1 : 0);
     uint32_t acc_par = 0, g_par = 0;  // g_par: bit b = parity of g_full[b]
+    WD_TR_DECL((e == 0 || e == 4) && lane == 0);   // one warp of column groups 0 and 1
+    const int tr_role = 1 + (e >> 2);
+    (void)tr_role;
 
     for (int tile = units->t_last; tile >= units->t_first; --tile) {
       const long long grow = (long long)tile * kWdM + row;
@@ -552,8 +584,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const uint32_t xb = xcnt & 1;
         mbar_wait(xa_empty + 8 * xb, ((xcnt >> 1) & 1) ^ 1);
         ++xcnt;
-        uint8_t* const xa_hi = xa + xb * WdSmem::xa_buf;
-        if (col0 < P.d) wd_store16(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, v, with_lo);
+        const uint32_t xa_hi = lane_addr + kWdTmXa + 64 * xb + 8 * cg;
+        if (col0 < P.d) wd_put16(xa_hi, xa_hi + 32, v, with_lo);
         wd_publish(xa_full + 8 * xb);
       }
       int until_keep = P.thin - ((P.step_base + s0) % P.thin), kept = (P.step_base + s0) / P.thin;
@@ -567,46 +599,52 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
         const long long xrow = (k == 0 && P.row_index && rv) ? P.row_index[grow] : grow;
         const bool final_x2 = P.x_out2 && (k == K - 1);
         // E1: z1 -> h1 (A of GEMM2); act'(z1) -> TMEM [256, 384)
+        WD_TR(tr_role, 1 * 256);
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
         tcgen05_fence_after();
+        WD_TR(tr_role, 2 * 256);
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
           f32x2 v[8], sd[8];
-          tmem_ld16p(lane_addr + 0 + hcol + 16 * blk, v);
+          tmem_ld16p(lane_addr + kWdTmZ1 + hcol + 16 * blk, v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) act2<ACT>(add2(v[i], b1[8 * blk + i]), v[i], sd[i]);
-          tmem_st16p(lane_addr + 256 + hcol + 16 * blk, sd);
-          wd_store16p(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          tmem_st16p(lane_addr + kWdTmZ1 + hcol + 16 * blk, sd);   // act'(z1) replaces z1 (each thread rewrites what it read)
+          wd_put16p(a_hi + 8 * blk, a_lo + 8 * blk, v, with_lo);
           wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E2: z2 -> delta2 = w3 * act'(z2) (A of GEMM3)
+        WD_TR(tr_role, 3 * 256);
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
         tcgen05_fence_after();
+        WD_TR(tr_role, 4 * 256);
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
           f32x2 v[8];
-          tmem_ld16p(lane_addr + 128 + hcol + 16 * blk, v);
+          tmem_ld16p(lane_addr + kWdTmZ2 + hcol + 16 * blk, v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             f32x2 hh, dh;
             act2<ACT>(add2(v[i], b2[8 * blk + i]), hh, dh);
             v[i] = mul2(dh, w3[8 * blk + i]);
           }
-          wd_store16p(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          wd_put16p(a_hi + 8 * blk, a_lo + 8 * blk, v, with_lo);
           wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E3: t -> delta1 = t * act'(z1) (A of every GEMM4 chunk)
+        WD_TR(tr_role, 5 * 256);
         mbar_wait(acc_bar, acc_par); acc_par ^= 1;
         tcgen05_fence_after();
+        WD_TR(tr_role, 6 * 256);
         tmem_st_wait();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
           f32x2 v[8], sd[8];
-          tmem_ld16p_nowait(lane_addr + 0 + hcol + 16 * blk, v);
-          tmem_ld16p(lane_addr + 256 + hcol + 16 * blk, sd);
+          tmem_ld16p_nowait(lane_addr + kWdTmT + hcol + 16 * blk, v);
+          tmem_ld16p(lane_addr + kWdTmZ1 + hcol + 16 * blk, sd);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = mul2(v[i], sd[i]);
-          wd_store16p(a_hi, a_lo, row, hcol + 16 * blk, v, with_lo);
+          wd_put16p(a_hi + 8 * blk, a_lo + 8 * blk, v, with_lo);
           wd_publish(wd_bar(smem, WdSmem::a_chunk + 2 * cg + blk));
         }
         // E4: per 64-column chunk: G_c -> Langevin update of the state chunk -> global + A operand of GEMM1'_c
@@ -618,6 +656,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           // the state chunk is requested first (an L2 hit from the previous step's store); the noise draw below
           // covers its latency
           float xc[16];
+          WD_TR(tr_role, 7 * 256 + c);
           if (active) wd_load_x16(xsrc, xrow, col0, P.d, rv, vec, xc);
           f32x2 eps[8];
           if (active) {
@@ -646,13 +685,15 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
               }
             }
           }
+          WD_TR(tr_role, 8 * 256 + c);
           mbar_wait(wd_bar(smem, WdSmem::g_full + (c & 1)), (g_par >> (c & 1)) & 1);
           g_par ^= 1u << (c & 1);
           tcgen05_fence_after();
+          WD_TR(tr_role, 9 * 256 + c);
           f32x2 X[8];
           if (active) {
             f32x2 g[8];
-            tmem_ld16p(lane_addr + 384 + 64 * (c & 1) + 16 * cg, g);
+            tmem_ld16p(lane_addr + kWdTmG + 64 * (c & 1) + 16 * cg, g);
             const float c12 = c1 * c2;
             // x' = (x - h g) + c2 c1 eps (base_integrator.py:728-729) on packed pairs; the fused roundings are within this
             // kernel's 2e-5 class
@@ -678,13 +719,17 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           // publish the new chunk to the tensor core first (GEMM1' of the next step is on the critical path), then
           // let the global stores drain underneath the next chunk's noise draw
           const uint32_t xb = xcnt & 1;
+          WD_TR(tr_role, 10 * 256 + c);
           mbar_wait(xa_empty + 8 * xb, ((xcnt >> 1) & 1) ^ 1);
           ++xcnt;
+          WD_TR(tr_role, 11 * 256 + c);
           if (active) {
-            uint8_t* const xa_hi = xa + xb * WdSmem::xa_buf;
-            wd_store16p(xa_hi, xa_hi + WdSmem::xa_buf / 2, row, 16 * cg, X, with_lo);
+            const uint32_t xa_hi = lane_addr + kWdTmXa + 64 * xb + 8 * cg;
+            wd_put16p(xa_hi, xa_hi + 32, X, with_lo);
           }
+          WD_TR(tr_role, 12 * 256 + c);
           wd_publish(xa_full + 8 * xb);
+          WD_TR(tr_role, 13 * 256 + c);
           if (active) {
             wd_store_x16(P.x_out, grow * P.d, col0, P.d, rv, vec, xc);
             if (final_x2) wd_store_x16(P.x_out2, grow * P.d, col0, P.d, rv, vec, xc);
@@ -1020,3 +1065,10 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
 }
 
 }  // namespace ebm
+
+#ifdef EBM_WD_TRACE
+extern "C" int ebm_debug_wd_trace(unsigned long long* out, int n) {
+  const size_t bytes = sizeof(unsigned long long) * (size_t)(n < 4 * ebm::kWdTraceLen ? n : 4 * ebm::kWdTraceLen);
+  return (int)cudaMemcpyFromSymbol(out, ebm::g_wd_trace, bytes);
+}
+#endif
