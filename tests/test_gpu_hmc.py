@@ -326,3 +326,44 @@ def test_hmc_tc_balanced_proposal_split_is_bit_identical():
         assert torch.equal(a, b)
     acc = outs[0][1]
     assert bool((acc <= n).all()) and int(acc.sum()) > 0.3 * n * k
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_hmc_mlp_force_is_recomputed_after_sanitising(precision):
+    """leapfrog.py:160-185: the reference evaluates the drift at the top of EVERY step, so after nan_to_num_ rewrote a
+    coordinate of x the next half-kick uses the force at the sanitised state, and hmc.py:266 takes E(x') there.  The
+    tensor-core kernel carries the force across steps; a sanitising event makes the tile redo the proposal without
+    carrying.  Rows 3 and 200 get a momentum that overflows two coordinates to +inf / -inf in the first drift: hidden
+    units whose two weights share a sign see inf - inf, the whole force is NaN, the bottom half sanitises (p -> 0,
+    x -> +-FLT_MAX in the two coordinates), and from there the reference continues with finite forces and ACCEPTS
+    (K0 = inf clamps to 1e10).  With a stale NaN force the row would end NaN and be rejected."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    torch.manual_seed(12)
+    n, d, L, k = 300, 24, 3, 2
+    mlp = te.MLPEnergy(dim=d, hidden=(48, 40), activation="tanh", precision=precision).to(DEV)
+    lin = [l for l in mlp.net if isinstance(l, torch.nn.Linear)]
+    en_cpu = E.MLP([l.weight.cpu() for l in lin], [l.bias.cpu() for l in lin], "tanh")
+    x0 = torch.randn(n, d)
+    noise_p, noise_u = torch.randn(k, n, d), torch.rand(k, n)
+    special = [3, 200]
+    for r in special:
+        noise_p[0, r, 5] = 3.0e38
+        noise_p[0, r, 11] = -3.0e38
+    h = 4.0   # h * p overflows for the two coordinates; every other chain just takes large steps
+    desc = te.energy_descriptor(mlp, d, torch.device(DEV))
+    acc = torch.zeros(k, dtype=torch.int32, device=DEV)
+    got = ops.hmc_burst(desc, x0.to(DEV), k, L, [h], rng_mode=_lib.RNG_INJECTED, noise_p=noise_p.to(DEV),
+                        noise_u=noise_u.to(DEV), accept_count=acc).cpu()
+    want, wdiag = ohmc.sample(en_cpu, x0, k, h, L, noise_p=noise_p, noise_u=noise_u, return_diagnostics=True)
+    assert torch.isfinite(want).all() and torch.isfinite(got).all()
+    fmax = torch.finfo(torch.float32).max
+    for r in special:   # the oracle accepted the sanitised trajectory of proposal 0
+        assert want[r].abs().max().item() == fmax
+        assert got[r, 5].abs().item() == fmax and got[r, 11].abs().item() == fmax, got[r]
+    mag = want.abs().clamp(min=1.0)
+    bad = (((got - want).abs() / mag).amax(dim=1) > 1e-3).float().mean().item()
+    assert bad < 0.02, bad   # large steps: a few borderline accept decisions may flip
+    assert not bool((((got[special] - want[special]).abs() / mag[special]).amax(dim=1) > 1e-3).any())
+    torch.testing.assert_close(acc.float().cpu() / n, wdiag["acceptance_rate"], atol=0.02, rtol=0)

@@ -296,13 +296,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_tc_kernel(const __
 // leapfrog kicks / drift instead of the Langevin update, with the momentum parked in TMEM columns [384, 512); after
 // evaluation L the four column-quarter warps of a row combine their partial energies through shared memory (one named
 // barrier per proposal) and every thread takes the Metropolis decision of its row.  The pre-proposal state is parked
-// in x_out.  Deviation from the reference in one corner: when safe-mode sanitising rewrites a NaN/inf coordinate the
-// reference recomputes the force at the sanitised state before the next step; here the carried force is kept.
+// in x_out.  Force carrying is exact as long as safe-mode sanitising leaves x alone (the reference evaluates the drift
+// at the top of every step, leapfrog.py:160: at an unchanged x that is the value carried from the bottom of the previous
+// step).  When nan_to_num rewrites a coordinate of x the carried force is stale, and E(x') has to be taken at the
+// sanitised state: the thread that sees it posts a token, and after the proposal's last evaluation the whole tile
+// REDOES the proposal the reference's way -- same momentum (counter-based draw), no carrying: per step one evaluation
+// for the top half-kick and drift, one for the bottom half-kick and sanitising, and a final forward pass for E(x') --
+// 2L + 1 evaluations, the MMA warp learning the verdict through one mbarrier per proposal.  Rows that never tripped
+// get the same trajectory again (the recomputed forces are bit-identical to the carried ones).
 struct TcHmcParams {
   MlpSchedule sched;   // balanced (tile, proposal) split (the copy the kernel reads; T.sched is unused here)
   TcParams T;          // weights, widths, passes; T.n_steps = proposals of this launch * (L + 1)
   HmcParams H;
 };
+
+__device__ __forceinline__ int hmc_redo_token(int tile, int ip, int n_prop) {   // unique per (tile, proposal) of a launch; never 0
+  return (int)((((long long)tile * n_prop + ip) & 0x3fffffff) + 1);
+}
 
 template <int ACT>
 __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_constant__ TcHmcParams Q,
@@ -317,6 +327,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int c = 0; c < kTcChunks; ++c) mbar_init(smem_u32(smem + TcSmemLayout::bars + c * 8), 4);
     mbar_init(smem_u32(smem + TcSmemLayout::bars + kTcChunks * 8), 1);
+    mbar_init(smem_u32(smem + TcSmemLayout::hmc_verdict), 1);
+    *reinterpret_cast<volatile int*>(smem + TcSmemLayout::hmc_redo) = 0;
     fence_mbar_init();
   }
   // work quantum = one proposal of one tile: a tile's proposals may be split between two CTAs (mlp_schedule.cuh); only
@@ -335,14 +347,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
   if (warp < kTcRoleWarps) {
     if (warp == 0) {   // converged: all lanes wait, one elected lane issues (umma.cuh: elect_one)
       const bool leader = elect_one();
-      uint32_t parity = 0;
-      for (int tile = units->t_last; tile >= units->t_first; --tile) {
-        const int n_evals = (mlp_unit_s1(units, tile, H.n_prop) - mlp_unit_s0(units, tile)) * (L + 1);
+      uint32_t parity = 0, vpar = 0;
+      auto evaluations = [&](int n_evals) {
         for (int k = 0; k < n_evals; ++k) {
           tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, false, k1, P.passes, parity, leader); parity ^= 1;
           tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, false, k2, P.passes, parity, leader); parity ^= 1;
           tc_issue_gemm(smem, tmem + 0, TcSmemLayout::w2_hi, TcSmemLayout::w2_lo, true, k3, P.passes, parity, leader); parity ^= 1;
           tc_issue_gemm(smem, tmem + 128, TcSmemLayout::w1_hi, TcSmemLayout::w1_lo, true, k2, P.passes, parity, leader); parity ^= 1;
+        }
+      };
+      for (int tile = units->t_last; tile >= units->t_first; --tile) {
+        const int s0 = mlp_unit_s0(units, tile), s1 = mlp_unit_s1(units, tile, H.n_prop);
+        for (int ip = s0; ip < s1; ++ip) {
+          evaluations(L + 1);
+          // the epilogue's verdict on this proposal: redo it without force carrying?
+          mbar_wait(smem_u32(smem + TcSmemLayout::hmc_verdict), vpar); vpar ^= 1;
+          if (*reinterpret_cast<volatile int*>(smem + TcSmemLayout::hmc_redo) == hmc_redo_token(tile, ip, H.n_prop))
+            evaluations(2 * L + 1);
         }
       }
     }
@@ -403,6 +424,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
         float* e1p = pp + (1 * 4 + cq) * kTcM;
         float* k0p = pp + (2 * 4 + cq) * kTcM;
         float* k1p = pp + (3 * 4 + cq) * kTcM;
+        const int redo_token = hmc_redo_token(tile, ip, H.n_prop);
+        volatile int* redo_flag = reinterpret_cast<volatile int*>(smem + TcSmemLayout::hmc_redo);
+        bool slow = false;   // second pass of this proposal: no force carrying (header comment)
+        for (;;) {
         // park the pre-proposal state, draw the momentum (hmc.py:245 / :92-134) into TMEM, K(p) partial
         {
           tc_store_row32(H.x_out, grow, H.d, col_base, rv, x);
@@ -445,8 +470,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
           }
           k0p[row] = ksum;
         }
-        for (int l = 0; l <= L; ++l) {
-          const bool want_e = (l == 0) || (l == L);
+        const int n_ev = slow ? 2 * L + 1 : L + 1;
+        for (int l = 0; l < n_ev; ++l) {
+          const bool want_e = (l == 0) || (l == n_ev - 1);
           // E1: z1 -> h1 ; act'(z1) -> TMEM [256, 384)   (E1-E3 on packed fp32x2 pairs, as in langevin_mlp_tc_kernel)
           mbar_wait(acc_bar, parity); parity ^= 1;
           tcgen05_fence_after();
@@ -509,6 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
           float ksum = 0.0f;
           // three straight-line variants: first evaluation (top of step 1), middle (bottom of step l + top of step l+1),
           // last (bottom of step L + kinetic energy) -- `l` is uniform, so this only removes per-element predication
+          bool dirty = false;   // sanitising rewrote a coordinate of x: the carried force is stale from here on
           auto e4 = [&](auto first_c, auto last_c, unsigned todo) {
             constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
 #pragma unroll
@@ -524,6 +551,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
                 float xv = x[16 * blk + i], p_ = pv[i];
                 if (!kFirst) {                     // bottom of step l: second half kick, then sanitise
                   p_ = __fadd_rn(p_, __fmul_rn(half_h, f));
+                  dirty = dirty || !(fabsf(xv) <= 3.402823466e+38f);
                   xv = nan_to_num0(xv);
                   p_ = nan_to_num0(p_);
                 }
@@ -602,21 +630,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) hmc_mlp_tc_kernel(const __grid_
             }
             return todo;
           };
-          unsigned todo = 3;
-          if (H.mass.kind == 0) {
-            if (l == 0) todo = e4_fast(std::true_type{}, std::false_type{});
-            else if (l < L) todo = e4_fast(std::false_type{}, std::false_type{});
-            else todo = e4_fast(std::false_type{}, std::true_type{});
+          // second pass (no carrying): even evaluations give the force of a step's top half (kick + drift), odd ones the
+          // force of its bottom half (kick + sanitising); evaluation 2L is only the forward pass for E(x')
+          auto e4_slow = [&](bool bottom, bool kin) {
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {   // (unrolled: x[] must keep static indices to stay in registers)
+              float g[16], pv[16];
+              tmem_ld16(lane_addr + 128 + 16 * blk, g);
+              tmem_ld16(lane_addr + 384 + 16 * blk, pv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int col = col_base + 16 * blk + i;
+                const float f = clamp_torch(-g[i], -kSafeClamp, kSafeClamp);
+                float xv = x[16 * blk + i];
+                float p_ = __fadd_rn(pv[i], __fmul_rn(half_h, f));
+                if (bottom) {
+                  xv = nan_to_num0(xv);
+                  p_ = nan_to_num0(p_);
+                  if (kin) ksum += kin_term(p_, col);
+                } else {
+                  xv = __fadd_rn(xv, mass_div(__fmul_rn(h, p_), col));
+                }
+                const bool in = rv && col < H.d;
+                x[16 * blk + i] = in ? xv : 0.0f;
+                pv[i] = in ? p_ : 0.0f;
+              }
+              tmem_st16(lane_addr + 384 + 16 * blk, pv);
+              store_a_16(smem, row, col_base + 16 * blk, x + 16 * blk, with_lo);
+              tcgen05_fence_before();
+              signal_one(smem, first_chunk + blk, lane);
+            }
+          };
+          if (slow) {
+            if (l < 2 * L) e4_slow((l & 1) != 0, l == 2 * L - 1);
+            if (l == 2 * L - 1) k1p[row] = ksum;
+          } else {
+            unsigned todo = 3;
+            if (H.mass.kind == 0) {
+              if (l == 0) todo = e4_fast(std::true_type{}, std::false_type{});
+              else if (l < L) todo = e4_fast(std::false_type{}, std::false_type{});
+              else todo = e4_fast(std::false_type{}, std::true_type{});
+            }
+            if (todo) {
+              if (l == 0) e4(std::true_type{}, std::false_type{}, todo);
+              else if (l < L) e4(std::false_type{}, std::false_type{}, todo);
+              else e4(std::false_type{}, std::true_type{}, todo);
+            }
+            if (dirty) *redo_flag = redo_token;
+            if (l == L) k1p[row] = ksum;
           }
-          if (todo) {
-            if (l == 0) e4(std::true_type{}, std::false_type{}, todo);
-            else if (l < L) e4(std::false_type{}, std::false_type{}, todo);
-            else e4(std::false_type{}, std::true_type{}, todo);
-          }
-          if (l == L) k1p[row] = ksum;
         }
-        // all four column quarters of every row have written their partial sums
+        // all four column quarters of every row have written their partial sums (and any redo token)
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kTcEpiWarps) : "memory");
+        if (slow) break;
+        if (e == 0 && lane == 0) mbar_arrive(smem_u32(smem + TcSmemLayout::hmc_verdict));
+        if (*redo_flag != redo_token) break;
+        slow = true;   // restart from the parked pre-proposal state; the momentum draw repeats itself (counter-based)
+        tc_load_row32(H.x_out, grow, H.d, col_base, rv, x);
+        store_a_cols(smem, row, col_base, x, with_lo);
+        signal_cols(smem, first_chunk, lane);
+        }
         float e0 = b3, e1 = b3, kk0 = 0.0f, kk1 = 0.0f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {

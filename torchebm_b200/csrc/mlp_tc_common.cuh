@@ -74,12 +74,27 @@ struct TcSmemLayout {
   static constexpr int total = units + 16;
   // HMC kernel only: per-row partial sums of E(x), E(x'), K(p), K(p') per column quarter, double-buffered by proposal
   static constexpr int hmc_part = (total + 15) & ~15;
-  static constexpr int hmc_total = hmc_part + 2 * 4 * 4 * kTcM * 4;
+  // HMC kernel only: "this proposal must be redone without force carrying" token + the mbarrier that hands the
+  // epilogue's verdict to the MMA warp (hmc_mlp_tc_kernel)
+  static constexpr int hmc_redo = hmc_part + 2 * 4 * 4 * kTcM * 4;
+  static constexpr int hmc_verdict = hmc_redo + 8;
+  static constexpr int hmc_total = hmc_verdict + 8;
 };
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// bf16x2 word (low half = a) rounded to nearest, except that a FINITE value above the largest bf16 (it would round to
+// inf, and inf - inf in the residual would poison the whole row: safe-mode HMC sanitises +-inf to +-FLT_MAX,
+// base_integrator.py:879-889) keeps its truncated leading part; the residual carries the rest
+__device__ __forceinline__ uint32_t bf16x2_rn_finite(float a, float b) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+  uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+  if ((hu & 0x7fffu) == 0x7f80u && fabsf(a) <= 3.402823466e+38f) hu = (hu & 0xffff0000u) | (__float_as_uint(a) >> 16);
+  if ((hu & 0x7fff0000u) == 0x7f800000u && fabsf(b) <= 3.402823466e+38f) hu = (hu & 0x0000ffffu) | (__float_as_uint(b) & 0xffff0000u);
+  return hu;
 }
 
 // write kTcCols consecutive columns [col0, col0 + 32) of row r of the A operand (hi and lo copies); 8 columns = one
@@ -91,8 +106,7 @@ __device__ __forceinline__ void store_a_cols(uint8_t* smem, int r, int col0, con
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float a = v[oct * 8 + 2 * j], b = v[oct * 8 + 2 * j + 1];
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+      const uint32_t hu = bf16x2_rn_finite(a, b);
       ph[j] = hu;
       const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
       pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
@@ -111,8 +125,7 @@ __device__ __forceinline__ void store_a_16(uint8_t* smem, int r, int col0, const
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float a = v[oct * 8 + 2 * j], b = v[oct * 8 + 2 * j + 1];
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-      const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+      const uint32_t hu = bf16x2_rn_finite(a, b);
       ph[j] = hu;
       const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hu << 16), b - __uint_as_float(hu & 0xffff0000u));
       pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
