@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EBM_ABI_VERSION 8
+#define EBM_ABI_VERSION 9
 
 #define EBM_ERR_INVALID     (-1) /* bad argument (null pointer, non-positive size, ...) */
 #define EBM_ERR_UNSUPPORTED (-2) /* valid request this build has no kernel for (e.g. dim too large) */
@@ -68,6 +68,9 @@ typedef struct EbmEnergyDesc {
   int32_t sm_margin;    /* MLP: SMs the persistent burst kernels leave free (0 = use all).  A burst that runs next to
                            a collective on another stream needs >= 1: its CTAs fill every SM they get, and a barrier or
                            copy kernel of the collective would otherwise wait for the whole burst. */
+  int32_t hidden3;      /* MLP: H3 > 0 = three hidden layers, E = w4 . act(W3 act(W2 act(W1 x + b1) + b2) + b3) + b4
+                           (benchmarks/distributed_fsdp2.py:43-53); 0 = two hidden layers */
+  int32_t reserved;     /* 0 */
   /* scalar parameters (fp32, already rounded the way torch rounds the Python doubles):
    *   DoubleWell: p[0] = barrier_height, p[1] = b*b
    *   Harmonic  : p[0] = 0.5*k
@@ -78,12 +81,16 @@ typedef struct EbmEnergyDesc {
    *   MoG     : buf[0] = means[K,D], buf[1] = sigmas[K], buf[2] = weights[K]
    *   MLP     : buf[0] = W1[H1,D], buf[1] = b1[H1], buf[2] = W2[H2,H1], buf[3] = b2[H2],
    *             buf[4] = w3[H2], buf[5] = b3[1]            (torch [out,in] layout);
+   *             three hidden layers (hidden3 > 0): buf[4] = w4[H3], buf[5] = b4[1] (the output layer),
+   *             buf[7] = W3[H3,H2], buf[8] = b3[H3]; every width <= 128; the Langevin burst (tensor cores, precision
+   *             BF16X3 / BF16), ebm_energy_f32, ebm_gradient_f32 and the persistent-CD entry points take it, the
+   *             fused HMC kernels do not (EBM_ERR_UNSUPPORTED);
    *             buf[6] = scratch workspace of ebm_workspace_bytes() bytes, 128-byte aligned, used by the
    *             Langevin burst: hand-over flags of the balanced (tile, step-range) work split and, when D > 128,
    *             the per-call bf16 hi/lo re-split of the weights.  Required when D > 128; optional (NULL = whole
    *             tiles per SM, no balancing) when D <= 128.  One workspace must not be shared by bursts running
    *             concurrently on different streams.   */
-  const float* buf[8];
+  const float* buf[10];
 } EbmEnergyDesc;
 
 int         ebm_abi_version(void);

@@ -51,7 +51,7 @@ def energy_for(name, g):
         return E.Gaussian(g["mean"], g["cov"])
     if "mog" in name:
         return E.MixtureOfGaussians(g["means"], g["sigmas"], g["weights"])
-    if "mlp_tanh" in name:
+    if "mlp_tanh" in name or "mlp_deep" in name:
         return mlp_from(g, "tanh")
     if "mlp" in name:
         return mlp_from(g, "silu")
@@ -69,7 +69,7 @@ LANGEVIN_CASES = [
     "langevin_doublewell", "langevin_doublewell_odd", "langevin_doublewell_k100", "langevin_harmonic",
     "langevin_rastrigin", "langevin_gaussian_c1", "langevin_gaussian_d16", "langevin_single_chain",
     "langevin_scheduled", "langevin_mlp_silu", "langevin_mlp_tanh", "langevin_mlp_d128", "langevin_mog",
-    "langevin_mlp_d784",
+    "langevin_mlp_d784", "langevin_mlp_deep",
 ]
 # cases whose closed-form gradient is bit-identical to the reference's autograd on CPU
 LANGEVIN_BITEXACT_CLOSED = {

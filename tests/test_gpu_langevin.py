@@ -36,8 +36,10 @@ def _model_for(name, g):
         return te.GaussianModel(g["mean"], g["cov"]).to(DEV)
     if "mog" in name:
         return te.MixtureOfGaussiansModel(g["means"], g["sigmas"], g["weights"]).to(DEV)
-    act = "tanh" if "tanh" in name else "silu"
+    act = "tanh" if ("tanh" in name or "deep" in name) else "silu"
     d, h = g["w0"].shape[1], g["w0"].shape[0]
+    if "w3" in g:   # three hidden layers
+        h = (g["w0"].shape[0], g["w1"].shape[0], g["w2"].shape[0])
     m = te.MLPEnergy(dim=d, hidden=h, activation=act)
     lin = [l for l in m.net if isinstance(l, torch.nn.Linear)]
     with torch.no_grad():
@@ -542,3 +544,59 @@ def test_heun_burst_matches_reference_golden_and_stream(name):
     bg = olang.sample(E.Gaussian(torch.zeros(6), torch.eye(6) * 2.0).to(DEV), xg, 5, 0.01, 1.0,
                       generator=torch.Generator(DEV).manual_seed(6), scheme="heun")
     torch.testing.assert_close(ag, bg, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("act,dims", [("silu", (128, 128, 128, 128)), ("tanh", (100, 96, 128, 40)), ("softplus", (30, 17, 50, 128)),
+                                      ("relu", (64, 64, 64, 64))])
+def test_three_hidden_layer_mlp_kernel(act, dims):
+    """benchmarks/distributed_fsdp2.py:43-53: energies with three hidden layers run on their own tensor-core kernel
+    (csrc/ebm_mlp_deep.cu: three weight matrices fill shared memory, every A operand lives in tensor memory).  More
+    tiles than SMs with a ragged last one, ragged widths, clamp + thinned trajectory on the reference-identical torch
+    stream against the oracle on CUDA; energy / gradient entry points; native stream; balanced split = whole tiles; in
+    place; the persistent-CD one-call path; HMC takes the integrator-level path."""
+    import torchebm_b200 as te
+    from torchebm_b200 import _lib, ops
+
+    torch.manual_seed(2)
+    d, widths = dims[0], dims[1:]
+    model = te.MLPEnergy(dim=d, hidden=widths, activation=act).to(DEV)
+    lin = [l for l in model.net if isinstance(l, torch.nn.Linear)]
+    assert len(lin) == 4
+    en = E.MLP([l.weight for l in lin], [l.bias for l in lin], act)
+    n = 148 * 128 + 77 if act == "silu" else 700
+    x0 = torch.randn(n, d, device=DEV).clamp_(-3, 3)
+    keep = x0.clone()
+    desc = te.energy_descriptor(model, d, x0.device)
+    assert desc is not None and desc.c.hidden3 == widths[2] and desc.c.precision == _lib.MLP_BF16X3
+    s = te.LangevinDynamics(model, step_size=0.01, noise_scale=0.5, clamp=(-2.5, 2.5), device=DEV)
+    got = s.sample(x=x0, n_steps=6, thin=2, return_trajectory=True, generator=torch.Generator(DEV).manual_seed(9))
+    want = olang.sample(en, x0, 6, 0.01, 0.5, clamp=(-2.5, 2.5), thin=2, return_trajectory=True,
+                        generator=torch.Generator(DEV).manual_seed(9))
+    assert got.shape == (n, 3, d) and torch.equal(x0, keep)
+    if act == "relu":  # act' jumps at 0: a pre-activation within rounding of the kink may take the other branch
+        bad = ((got - want).abs() > 2e-5 + 1e-4 * want.abs()).float().mean().item()
+        assert bad < 1e-4, bad
+    else:
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(ops.gradient(desc, x0[:333]), en.gradient(x0[:333]), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(ops.energy(desc, x0[:333]), en.energy(x0[:333]).detach(), rtol=1e-5, atol=1e-4)
+    # native stream: deterministic; the balanced (tile, step-range) split equals whole tiles; in place
+    a = ops.langevin_burst(desc, x0, 5, [0.01], [0.5], rng_mode=_lib.RNG_NATIVE, seed=1, offset=0)
+    assert torch.isfinite(a).all()
+    d2 = te.energy_descriptor(model, d, x0.device)
+    d2.c.buf[6] = None
+    b = ops.langevin_burst(d2, x0, 5, [0.01], [0.5], rng_mode=_lib.RNG_NATIVE, seed=1, offset=0)
+    assert torch.equal(a, b)
+    x1 = x0.clone()
+    ops.langevin_burst(desc, x1, 5, [0.01], [0.5], rng_mode=_lib.RNG_NATIVE, seed=1, offset=0, out=x1)
+    assert torch.equal(x1, a)
+    # diagnostics through the sampler API
+    _, diag = s.sample(x=x0[:512], n_steps=4, thin=2, return_diagnostics=True, generator=torch.Generator(DEV).manual_seed(3))
+    _, wd = olang.sample(en, x0[:512], 4, 0.01, 0.5, clamp=(-2.5, 2.5), thin=2, return_diagnostics=True,
+                         generator=torch.Generator(DEV).manual_seed(3))
+    torch.testing.assert_close(diag["energy"], wd["energy"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(diag["mean"], wd["mean"], rtol=1e-4, atol=2e-5)
+    # HMC has no fused kernel for this energy: the integrator-level path still samples
+    hm = te.HamiltonianMonteCarlo(model, step_size=0.05, n_leapfrog_steps=3, device=DEV)
+    out = hm.sample(x=x0[:256], n_steps=2, generator=torch.Generator(DEV).manual_seed(4))
+    assert out.shape == (256, d) and torch.isfinite(out).all()

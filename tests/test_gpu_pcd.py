@@ -162,7 +162,7 @@ def test_c3_full_size_cd_step_properties():
 
 
 @pytest.mark.parametrize("d,buffer_size,batch", [(784, 300, 300), (784, 700, 300), (64, 33000, 33000), (64, 40000, 4096),
-                                                  (64, 100, 300)])
+                                                  (64, 100, 300), (64, 640, 640)])
 @pytest.mark.parametrize("rng", ["torch", "native"])
 @pytest.mark.parametrize("ratio", [0.0, 0.05, 0.25])
 def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rng, ratio):
@@ -174,7 +174,8 @@ def test_fused_pcd_negatives_equal_the_three_call_path(d, buffer_size, batch, rn
     import torchebm_b200 as te
 
     torch.manual_seed(3)
-    model = te.MLPEnergy(dim=d, hidden=(128, 96), activation="silu").to(DEV)
+    # (the 100- and 640-row cases cover the three-hidden-layer energy: its kernel reads start rows and writes back the same way)
+    model = te.MLPEnergy(dim=d, hidden=(128, 96, 64) if buffer_size in (100, 640) else (128, 96), activation="silu").to(DEV)
 
     def make():
         sampler = te.LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=DEV).with_rng(rng)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # EBM_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); still no fallback of any kind
 LIB_PATH = os.environ.get("EBM_B200_LIB") or os.path.join(HERE, "lib", "libebm_b200.so")
 
-EBM_ABI_VERSION = 8
+EBM_ABI_VERSION = 9
 
 ENERGY_DOUBLE_WELL, ENERGY_HARMONIC, ENERGY_RASTRIGIN, ENERGY_GAUSSIAN, ENERGY_MOG, ENERGY_MLP = range(6)
 ACT_SILU, ACT_TANH, ACT_RELU, ACT_SOFTPLUS = range(4)
@@ -37,8 +37,10 @@ class EbmEnergyDesc(C.Structure):
         ("activation", C.c_int32),
         ("precision", C.c_int32),
         ("sm_margin", C.c_int32),
+        ("hidden3", C.c_int32),
+        ("reserved", C.c_int32),
         ("p", C.c_float * 4),
-        ("buf", C.c_void_p * 8),
+        ("buf", C.c_void_p * 10),
     ]
 
 

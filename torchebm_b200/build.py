@@ -22,7 +22,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libebm_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["ebm_core.cu", "ebm_ess.cu", "ebm_hmc.cu", "ebm_mlp.cu", "ebm_mlp_tc.cu", "ebm_mlp_tc2.cu", "ebm_mlp_wide.cu"]
+SOURCES = ["ebm_core.cu", "ebm_ess.cu", "ebm_hmc.cu", "ebm_mlp.cu", "ebm_mlp_tc.cu", "ebm_mlp_tc2.cu", "ebm_mlp_wide.cu", "ebm_mlp_deep.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -369,7 +369,8 @@ _ACT_BY_NAME = {"silu": nn.SiLU, "tanh": nn.Tanh, "relu": nn.ReLU, "softplus": n
 
 class MLPEnergy(BaseModel):
     """`Sequential(Linear(D,H1), act, Linear(H1,H2), act, Linear(H2,1))` + `squeeze(-1)`: the MLP energies of
-    examples/20-training/01-mcmc-losses/01-cd-k/main.py:20-30 and benchmarks/registry.py:375-387.
+    examples/20-training/01-mcmc-losses/01-cd-k/main.py:20-30 and benchmarks/registry.py:375-387; with three hidden
+    widths (`hidden=(H1, H2, H3)`) the deeper energy of benchmarks/distributed_fsdp2.py:43-53.
     Pass an existing `nn.Sequential` as `net` to share its parameters."""
 
     def __init__(self, dim: Optional[int] = None, hidden: Union[int, Sequence[int]] = 128, activation: str = "silu",
@@ -385,32 +386,41 @@ class MLPEnergy(BaseModel):
         if net is None:
             if dim is None:
                 raise ValueError("dim must be given when net is None")
-            h1, h2 = (hidden, hidden) if isinstance(hidden, int) else tuple(hidden)
+            widths = (hidden, hidden) if isinstance(hidden, int) else tuple(hidden)
+            if len(widths) not in (2, 3):
+                raise ValueError("hidden must be an int or two or three widths")
             act = _ACT_BY_NAME[activation]
-            net = nn.Sequential(nn.Linear(dim, h1), act(), nn.Linear(h1, h2), act(), nn.Linear(h2, 1))
+            layers, prev = [], dim
+            for w in widths:
+                layers += [nn.Linear(prev, w), act()]
+                prev = w
+            net = nn.Sequential(*layers, nn.Linear(prev, 1))
         if _match_mlp(net) is None:
-            raise ValueError("net must be Sequential(Linear, act, Linear, act, Linear(., 1)) with SiLU/Tanh/ReLU/Softplus")
+            raise ValueError("net must be Sequential(Linear, act, Linear, act, [Linear, act,] Linear(., 1)) with "
+                             "SiLU/Tanh/ReLU/Softplus")
         self.net = net
 
     def forward(self, x):
         return self.net(x).squeeze(-1)
 
 
-def _match_mlp(net) -> Optional[Tuple[nn.Linear, nn.Linear, nn.Linear, int]]:
-    if not isinstance(net, nn.Sequential) or len(net) != 5:
+def _match_mlp(net) -> Optional[Tuple[List[nn.Linear], int]]:
+    """(the Linear layers in order -- two or three hidden ones and the scalar output layer --, activation code) of a
+    `Sequential(Linear, act, Linear, act, [Linear, act,] Linear(., 1))`, or None."""
+    if not isinstance(net, nn.Sequential) or len(net) not in (5, 7):
         return None
-    l1, a1, l2, a2, l3 = net
-    if not all(isinstance(l, nn.Linear) for l in (l1, l2, l3)):
+    lins, acts = list(net)[0::2], list(net)[1::2]
+    if not all(isinstance(l, nn.Linear) for l in lins):
         return None
-    if type(a1) is not type(a2) or type(a1) not in _ACT_CODES:
+    if any(type(a) is not type(acts[0]) for a in acts) or type(acts[0]) not in _ACT_CODES:
         return None
-    if isinstance(a1, nn.Softplus) and (a1.beta != 1.0 or a1.threshold != 20.0):
+    if any(isinstance(a, nn.Softplus) and (a.beta != 1.0 or a.threshold != 20.0) for a in acts):
         return None
-    if l3.out_features != 1 or l1.out_features != l2.in_features or l2.out_features != l3.in_features:
+    if lins[-1].out_features != 1 or any(a.out_features != b.in_features for a, b in zip(lins[:-1], lins[1:])):
         return None
-    if any(l.bias is None for l in (l1, l2, l3)):
+    if any(l.bias is None for l in lins):
         return None
-    return l1, l2, l3, _ACT_CODES[type(a1)]
+    return lins, _ACT_CODES[type(acts[0])]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -505,21 +515,28 @@ def energy_descriptor(model: nn.Module, dim: int, device) -> Optional[EnergyDesc
         m = _match_mlp(net)
         if m is None:
             return None
-        l1, l2, l3, act = m
+        lins, act = m
+        l1, l2, l_out = lins[0], lins[1], lins[-1]
+        deep = len(lins) == 4   # three hidden layers: on-chip tensor-core kernel (csrc/ebm_mlp_deep.cu), every width <= 128
         if l1.in_features != dim:
             return None
-        if max(l1.out_features, l2.out_features) > MLP_MAX_WIDTH or l1.in_features > MLP_MAX_DIM:
+        if max(l.out_features for l in lins[:-1]) > MLP_MAX_WIDTH or l1.in_features > (MLP_MAX_WIDTH if deep else MLP_MAX_DIM):
             return None  # no fused kernel: integrator-level path (own autograd + fused update)
-        ts = [_dev_f32(t, device) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight.reshape(-1), l3.bias)]
+        ts = [_dev_f32(t, device) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l_out.weight.reshape(-1), l_out.bias)]
         d.kind = _lib.ENERGY_MLP
         d.hidden1, d.hidden2, d.activation = l1.out_features, l2.out_features, act
         precision = getattr(model, "precision", "bf16x3")
-        if l1.in_features > MLP_MAX_WIDTH and precision == "fp32":
-            precision = "bf16x3"  # wide states have a tensor-core kernel only (same accuracy class as fp32)
+        if (l1.in_features > MLP_MAX_WIDTH or deep) and precision == "fp32":
+            precision = "bf16x3"  # wide states / three hidden layers have a tensor-core kernel only (same accuracy class as fp32)
         d.precision = _lib.MLP_PRECISIONS[precision]
         d.sm_margin = int(getattr(model, "sm_margin", 0))
         for i, t in enumerate(ts):
             d.buf[i] = t.data_ptr()
+        if deep:
+            w3, b3 = _dev_f32(lins[2].weight, device), _dev_f32(lins[2].bias, device)
+            d.hidden3 = lins[2].out_features
+            d.buf[7], d.buf[8] = w3.data_ptr(), b3.data_ptr()
+            ts += [w3, b3]
         ws_bytes = int(_lib.load().ebm_workspace_bytes(C.byref(d)))
         if ws_bytes > 0 and torch.device(device).type == "cuda":  # hand-over flags + (wide states) the bf16 weight re-split
             ws = _mlp_workspace(device, ws_bytes)

@@ -123,7 +123,8 @@ inline int validate_desc(const EbmEnergyDesc* e) {
       return 0;
     case EBM_ENERGY_MLP:
       for (int i = 0; i < 6; ++i) if (!e->buf[i]) { set_error("mlp needs W1,b1,W2,b2,w3,b3"); return EBM_ERR_INVALID; }
-      if (e->hidden1 <= 0 || e->hidden2 <= 0) { set_error("mlp hidden sizes must be positive"); return EBM_ERR_INVALID; }
+      if (e->hidden1 <= 0 || e->hidden2 <= 0 || e->hidden3 < 0) { set_error("mlp hidden sizes must be positive"); return EBM_ERR_INVALID; }
+      if (e->hidden3 > 0 && (!e->buf[7] || !e->buf[8])) { set_error("three-hidden-layer mlp needs W3 (buf[7]) and b3 (buf[8])"); return EBM_ERR_INVALID; }
       return 0;
     default: set_error("unknown energy kind %d", e->kind); return EBM_ERR_INVALID;
   }

@@ -578,7 +578,7 @@ int ebm_langevin_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_o
 // burst kernels with a peer-store epilogue: the elementwise kernel and the two tensor-core MLP kernels
 static bool burst_stores_to_peers(const EbmEnergyDesc* e) {
   return e->kind == EBM_ENERGY_DOUBLE_WELL || e->kind == EBM_ENERGY_HARMONIC || e->kind == EBM_ENERGY_RASTRIGIN ||
-         (e->kind == EBM_ENERGY_MLP && (e->precision == EBM_MLP_BF16X3 || e->precision == EBM_MLP_BF16));
+         (e->kind == EBM_ENERGY_MLP && e->hidden3 == 0 && (e->precision == EBM_MLP_BF16X3 || e->precision == EBM_MLP_BF16));
 }
 
 // every other burst kernel: copy-engine pushes of the finished shard into every gathered buffer
@@ -720,6 +720,10 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
     if (mc_ptr && e->dim > 128) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }   // (the wide kernel's pusher only)
     rc = langevin_dispatch(c);
     if (rc) return rc;
+    if (world > 0 && !burst_stores_to_peers(e)) {   // (the three-hidden-layer kernel has no peer-store epilogue)
+      rc = push_to_peers(x_out, (size_t)n * row_elems, peers, world, row_offset * row_elems, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
     if (new_ptr_host) *new_ptr_host = 0;
   } else if (ebm_pcd_langevin_fused(e) != 0 && idx != nullptr && n_noise == 0) {
     // the burst kernel reads its start rows through idx; the FIFO write-back stays a separate launch (a destination
@@ -730,6 +734,10 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
     if (mc_ptr && e->dim > 128) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }   // (the wide kernel's pusher only)
     rc = langevin_dispatch(c);
     if (rc) return rc;
+    if (world > 0 && !burst_stores_to_peers(e)) {   // (the three-hidden-layer kernel has no peer-store epilogue)
+      rc = push_to_peers(x_out, (size_t)n * row_elems, peers, world, row_offset * row_elems, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
     rc = ebm_pcd_scatter_f32(buffer, buffer_rows, row_elems, ptr, x_out, n, new_ptr_host, stream);
     if (rc) return rc;
   } else {   // gather (+ noise) -> burst -> FIFO scatter as separate launches

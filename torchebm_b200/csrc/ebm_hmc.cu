@@ -214,8 +214,8 @@ static int hmc_burst_impl(const EbmEnergyDesc* e, const float* x_in, float* x_ou
     case EBM_ENERGY_GAUSSIAN: return launch_hmc(make_gauss(e), c, P);
     case EBM_ENERGY_MOG: return launch_hmc(make_mog(e), c, P);
     case EBM_ENERGY_MLP:
-      if (e->dim > 128 || e->hidden1 > 128 || e->hidden2 > 128) {
-        set_error("hmc: MLP energies wider than 128 have no fused HMC kernel");
+      if (e->dim > 128 || e->hidden1 > 128 || e->hidden2 > 128 || e->hidden3 > 0) {
+        set_error("hmc: MLP energies wider than 128 or with three hidden layers have no fused HMC kernel");
         return EBM_ERR_UNSUPPORTED;
       }
       // bf16x3 (the default precision): tensor-core kernel, energies good to ~2e-5 relative; fp32: FFMA kernel; the

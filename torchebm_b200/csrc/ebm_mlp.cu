@@ -560,6 +560,11 @@ __global__ void __launch_bounds__(kMlpWarps * 32, 1) mlp_energy_grad_kernel(cons
 }
 
 static int fill_mlp(const EbmEnergyDesc* e, MlpParams& P) {
+  if (e->hidden3 > 0) {
+    set_error("three-hidden-layer MLP energies have no kernel for this operation (Langevin bursts with precision bf16x3 / bf16, "
+              "energy and gradient evaluation only)");
+    return EBM_ERR_UNSUPPORTED;
+  }
   if (e->dim > kMlpMax || e->hidden1 > kMlpMax || e->hidden2 > kMlpMax) {
     set_error("MLP energy %d->%d->%d->1: widths above %d are not supported by this build", e->dim, e->hidden1,
               e->hidden2, kMlpMax);
@@ -606,9 +611,12 @@ int hmc_mlp_launch(const EbmEnergyDesc* e, const HmcParams& P, const HStepTable&
 
 int mlp_wide_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                                   cudaStream_t st);  // ebm_mlp_wide.cu
+int mlp_deep_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
+                                  cudaStream_t st);  // ebm_mlp_deep.cu
 
 int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, float* energy, float* grad,
                              cudaStream_t st) {
+  if (e->hidden3 > 0) return mlp_deep_energy_grad_dispatch(e, x, n, energy, grad, st);
   if (e->dim > kMlpMax) return mlp_wide_energy_grad_dispatch(e, x, n, energy, grad, st);
   MlpParams P;
   int rc = fill_mlp(e, P);
@@ -628,8 +636,15 @@ int mlp_energy_grad_dispatch(const EbmEnergyDesc* e, const float* x, int64_t n, 
 
 int langevin_mlp_tc_dispatch(const LangevinCall& c, int passes);    // ebm_mlp_tc.cu
 int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes);  // ebm_mlp_wide.cu
+int langevin_mlp_deep_dispatch(const LangevinCall& c, int passes);  // ebm_mlp_deep.cu
 
 int langevin_mlp_dispatch(const LangevinCall& c) {
+  if (c.e->hidden3 > 0) {   // three hidden layers: tensor-core kernel with every A operand in tensor memory
+    if (c.e->precision == EBM_MLP_BF16X3) return langevin_mlp_deep_dispatch(c, 3);
+    if (c.e->precision == EBM_MLP_BF16) return langevin_mlp_deep_dispatch(c, 1);
+    set_error("three-hidden-layer MLP energies run on the tensor-core kernel only (precision bf16x3 or bf16)");
+    return EBM_ERR_UNSUPPORTED;
+  }
   if (c.e->dim > kMlpMax) {  // state wider than one tile: streamed-operand tensor-core kernel
     if (c.e->precision == EBM_MLP_BF16X3) return langevin_mlp_wide_dispatch(c, 3);
     if (c.e->precision == EBM_MLP_BF16) return langevin_mlp_wide_dispatch(c, 1);

@@ -194,7 +194,7 @@ class FusedHMCMixin(_RngAttribute):
         desc = energy_descriptor(self.model, d, self.device)
         if desc is None:
             return None
-        if desc.kind == "mlp" and (max(desc.c.dim, desc.c.hidden1, desc.c.hidden2) > 128
+        if desc.kind == "mlp" and (max(desc.c.dim, desc.c.hidden1, desc.c.hidden2) > 128 or desc.c.hidden3 > 0
                                    or desc.c.precision == _lib.MLP_BF16):
             return None   # no fused HMC kernel: wider MLP energies, single-pass bf16 (accept tests want fp32-grade energies)
         return desc, dim
