@@ -50,6 +50,8 @@ WORKLOADS = {
     "c2_traj": ("LangevinDynamics DoubleWell(2.0,1.0) dim=128 n_chains=65536 k=500, return_trajectory=True thin=1 "
                 "(16.8 GB trajectory written per burst)", 65536, 128, 500),
     "mlp128": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01", 65536, 128, 100),
+    "mlp128x3": ("LangevinDynamics MLP 128-128-128-128-1 (three hidden layers, benchmarks/distributed_fsdp2.py:43-53) SiLU "
+                 "n_chains=65536 k=100 step_size=0.01", 65536, 128, 100),
     "mlp128_fp32": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (fp32 FFMA kernel)", 65536, 128, 100),
     "mlp128_bf16": ("LangevinDynamics MLP 128-128-128-1 SiLU n_chains=65536 k=100 step_size=0.01 (single-pass bf16)", 65536, 128, 100),
     "c4": ("HamiltonianMonteCarlo Rastrigin(a=10) dim=64 n_chains=262144 L=20, 1 proposal per step, step_size=0.01", 262144, 64, 20),
@@ -293,8 +295,8 @@ def make_workload(name: str, n_local: int, dev, rng: str = "torch"):
         return step, desc, model, 8 * d, k
     if name.startswith("mlp128"):
         torch.manual_seed(0)
-        prec = {"mlp128": "bf16x3", "mlp128_fp32": "fp32", "mlp128_bf16": "bf16"}[name]
-        model = te.MLPEnergy(dim=d, hidden=128, activation="silu", precision=prec).to(dev)
+        prec = {"mlp128": "bf16x3", "mlp128x3": "bf16x3", "mlp128_fp32": "fp32", "mlp128_bf16": "bf16"}[name]
+        model = te.MLPEnergy(dim=d, hidden=(128, 128, 128) if name == "mlp128x3" else 128, activation="silu", precision=prec).to(dev)
         desc = te.energy_descriptor(model, d, dev)
         inc = ops.rng_consumed_langevin(dev, n_local * d, k, _lib.RNG_NATIVE)
 
@@ -616,7 +618,7 @@ def run_ours(args):
         # caps the torch-layout strong scaling at 86.5 % for 65 536 / N chains
         extra["native_rng"] = measure("c2", args.steps, args.warmup, rank, world, local, rng="native", nccl_gather=args.nccl_gather)
         sec_steps = max(5, min(args.steps, 10))
-        secondary = ["mlp128", "c3", "c4", "hmc_mlp128", "c2_traj"] if world == 1 else ["c5"]
+        secondary = ["mlp128", "mlp128x3", "c3", "c4", "hmc_mlp128", "c2_traj"] if world == 1 else ["c5"]
         extra["secondary"] = {w: measure(w, sec_steps, 3, rank, world, local, rng="torch" if w == "c2_traj" else "native")
                               for w in secondary}
     if rank != 0:
@@ -688,7 +690,7 @@ def roofline(workload, peaks, peak_kind, achieved_gbs, traffic, algo_bytes, kern
                              "the algorithmic FLOP counted here"}
     if workload.startswith("mlp128") or workload in ("c3", "c5"):
         d_in = 784 if workload in ("c3", "c5") else 128
-        flops = 4 * (d_in * 128 + 128 * 128 + 128) * units_per_launch
+        flops = 4 * (d_in * 128 + (2 if workload == "mlp128x3" else 1) * 128 * 128 + 128) * units_per_launch
         ach = flops / (kernel_ms * 1e-3) / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_kind": peak_kind + " (cuBLAS bf16 burst)",
@@ -713,7 +715,7 @@ def _reference_langevin(ref, workload: str, device):
     elif workload == "c2":
         model = DoubleWellModel(barrier_height=2.0, b=1.0).to(device)   # (BaseModel.gradient moves x to the MODEL's device)
     else:
-        model = _RefMLP(784 if workload in ("c3", "c5") else 128).to(device)
+        model = _RefMLP(784 if workload in ("c3", "c5") else 128, 3 if workload == "mlp128x3" else 2).to(device)
     return LangevinDynamics(model, step_size=0.01, noise_scale=1.0, device=device)
 
 
@@ -724,11 +726,14 @@ def _ref_mlp_class():
         """The reference's MLP energy (examples/20-training/01-mcmc-losses/01-cd-k/main.py:20-30), default nn.Linear init
         under torch.manual_seed(0); gradient = the reference's own autograd `BaseModel.gradient`."""
 
-        def __init__(self, dim: int):
+        def __init__(self, dim: int, n_hidden: int = 2):
             super().__init__()
             torch.manual_seed(0)
-            self.net = torch.nn.Sequential(torch.nn.Linear(dim, 128), torch.nn.SiLU(), torch.nn.Linear(128, 128), torch.nn.SiLU(),
-                                           torch.nn.Linear(128, 1))
+            layers, prev = [], dim
+            for _ in range(n_hidden):
+                layers += [torch.nn.Linear(prev, 128), torch.nn.SiLU()]
+                prev = 128
+            self.net = torch.nn.Sequential(*layers, torch.nn.Linear(128, 1))
 
         def forward(self, x):
             return self.net(x).squeeze(-1)
@@ -736,13 +741,15 @@ def _ref_mlp_class():
     return RefMLP
 
 
-def _RefMLP(dim: int):
-    return _ref_mlp_class()(dim)
+def _RefMLP(dim: int, n_hidden: int = 2):
+    return _ref_mlp_class()(dim, n_hidden)
 
 
 def _oracle_energy(workload, device="cpu"):
     from oracle import energies as E
 
+    if workload == "mlp128x3":
+        return E.make_mlp(128, (128, 128, 128), "silu", seed=0).to(device)
     if workload.startswith("mlp128"):
         return E.make_mlp(128, (128, 128), "silu", seed=0).to(device)
     if workload in ("c3", "c5"):
