@@ -34,6 +34,7 @@ struct DeepSmem {
 };
 static_assert(DeepSmem::total <= 232448, "shared memory budget of one sm_100 CTA exceeded");
 
+constexpr int kDpRoleRegs = 32, kDpEpiRegs = 112;
 constexpr uint32_t kDpR0 = 0, kDpR1 = 128, kDpR2 = 256, kDpA = 384, kDpALo = 448;
 
 struct DeepParams {
@@ -170,6 +171,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_deep_kernel(const 
   const volatile MlpUnits* units = reinterpret_cast<const volatile MlpUnits*>(smem + DeepSmem::units);
 
   if (warp < kTcRoleWarps) {
+    // 640 threads launch with 96 registers; the role warpgroup keeps 32, the four epilogue warpgroups take 112
+    // (128 * 32 + 512 * 112 = 640 * 96): the update epilogue holds the state, an accumulator block and the noise
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kDpRoleRegs));
     if (warp == 0) {   // converged: all lanes wait, one elected lane issues (umma.cuh: elect_one)
       const bool leader = elect_one();
       uint32_t parity = 0;
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) langevin_mlp_deep_kernel(const 
     }
   } else {
     // ---- epilogue warps: packed fp32x2 arithmetic, padded rows / columns computed like real ones and never stored ----
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kDpEpiRegs));
     const int e = warp - kTcRoleWarps;
     const int row = 32 * (warp & 3) + lane;        // TMEM lane this thread may access (hardware: warp % 4)
     const int cq = e >> 2;                          // column quarter
