@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the fused MCMC negative-sampling hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5|mlp128|hmc_mlp128]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5|mlp128|mlp128x3|hmc_mlp128]
 
 One bench "step" = one pass of the hot path over one batch: a K-step fused burst through the sampler-level
 API (`ops.langevin_burst` / `ops.hmc_burst`, i.e. one C-ABI call, one kernel launch).  Headline workload =
@@ -16,7 +16,7 @@ bit with an NCCL all-gather of the local results ("gather_check"); a mismatch fa
 
 The default line (no --workload) also carries, measured in the same process:
   "native_rng"  the same C2 run with the layout-native Philox stream (no padding to torch's 4*T-element blocks),
-  "secondary"   N = 1: mlp128 (the north_star MLP target), c3, c4;  N > 1: c5 (weak scaling, with its own gather_check),
+  "secondary"   N = 1: mlp128 (the north_star MLP target), mlp128x3, c3, c4;  N > 1: c5 (weak scaling, with its own gather_check),
   "torch_cuda_baseline" / "triton_poc" / "cpu_baseline": the UNMODIFIED reference (baseline/_ref) on the same GPU, its
   Triton proof-of-concept kernel (torchebm/cuda/fused_langevin.py:141-180) on C2, and its CPU path on the host cores.
 
@@ -538,7 +538,10 @@ def measure(workload: str, steps: int, warmup: int, rank: int, world: int, local
 
     if fused_gather:
         collective = ("burst-end gather fused into the kernel's final store (" +
-                      ("one NVLS multicast store per 16 bytes, replicated by NVSwitch into every rank's symmetric buffer"
+                      ("two pusher warps per SM move every finished tile with 8 KB bulk copies, x_out -> shared memory -> one bulk "
+                       "store per peer mapping of the symmetric buffers"
+                       if (workload == "c5" and os.environ.get("EBM_B200_PUSH_BULK", "1") != "0") else
+                       "one NVLS multicast store per 16 bytes, replicated by NVSwitch into every rank's symmetric buffer"
                        if (peer.mc_ptr and workload == "c5") else "NVLink peer stores into symmetric memory") + ") + device-side barrier")
     elif world == 1:
         collective = "none"

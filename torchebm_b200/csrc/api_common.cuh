@@ -172,6 +172,14 @@ struct LangevinCall {
   int peer_mc;
 };
 
+// Form of the wide MLP kernel's burst-end gather (ebm_mlp_wide.cu): bulk copies x_out -> shared memory -> every peer
+// mapping (default; measured best at 2 and at 8 GPUs), or with EBM_B200_PUSH_BULK=0 16-byte stores -- through the NVLS
+// multicast address when the caller passes one, else one per peer.
+inline int wide_push_bulk() {
+  static const int v = [] { const char* s = getenv("EBM_B200_PUSH_BULK"); return (s && s[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
 // diagnostics helpers shared by the Langevin and HMC entry points (ebm_core.cu)
 // ws slot += column sums / sums of squares of x[n, d] and the sum of energy[n] (energy may be null)
 int diag_accumulate(double* ws_slot, const float* x, const float* energy, int64_t n, int d, cudaStream_t st);

@@ -613,7 +613,7 @@ int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, flo
                  fused ? peer_out_host : nullptr, fused ? world : 0, row_offset, 0};
   // multicast only where it wins (measured at 8 GPUs): the wide MLP kernel's coalesced pusher.  The elementwise kernel's
   // final store is already one coalesced store per peer, and the native-stream C2 run was 3 % faster with those.
-  if (fused && multicast && e->kind == EBM_ENERGY_MLP && e->dim > 128) { c.peers = peer_out_host + world; c.n_peers = 1; c.peer_mc = 1; }
+  if (fused && multicast && e->kind == EBM_ENERGY_MLP && e->dim > 128 && !wide_push_bulk()) { c.peers = peer_out_host + world; c.n_peers = 1; c.peer_mc = 1; }
   rc = langevin_dispatch(c);
   if (rc || fused) return rc;
   return push_to_peers(x_out, (size_t)n * e->dim, peer_out_host, world, row_offset * e->dim, (cudaStream_t)stream);
@@ -717,7 +717,7 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
     LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                    rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, nullptr, buffer, 0, 0, peers, world,
                    row_offset, 0, nullptr};
-    if (mc_ptr && e->dim > 128) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }   // (the wide kernel's pusher only)
+    if (mc_ptr && e->dim > 128 && !wide_push_bulk()) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }   // (the wide kernel's 16-byte-store pusher only)
     rc = langevin_dispatch(c);
     if (rc) return rc;
     if (world > 0 && !burst_stores_to_peers(e)) {   // (the three-hidden-layer kernel has no peer-store epilogue)
@@ -731,7 +731,7 @@ static int pcd_langevin_burst_impl(const EbmEnergyDesc* e, float* buffer, int64_
     LangevinCall c{e, buffer, x_out, n, n_steps, step_size_host, noise_scale_host, schedule_len, clamp_lo_hi_host,
                    rng_mode, seed, offset, nullptr, nullptr, 1, (cudaStream_t)stream, (const long long*)idx, nullptr, 0, 0,
                    peers, world, row_offset, 0, nullptr};
-    if (mc_ptr && e->dim > 128) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }   // (the wide kernel's pusher only)
+    if (mc_ptr && e->dim > 128 && !wide_push_bulk()) { c.peers = mc_ptr; c.n_peers = 1; c.peer_mc = 1; }   // (the wide kernel's 16-byte-store pusher only)
     rc = langevin_dispatch(c);
     if (rc) return rc;
     if (world > 0 && !burst_stores_to_peers(e)) {   // (the three-hidden-layer kernel has no peer-store epilogue)

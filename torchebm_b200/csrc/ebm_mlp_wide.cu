@@ -48,6 +48,7 @@ constexpr int kWdThreads = 32 * (kWdRoleWarps + kWdEpiWarps);
 constexpr int kWdRoleRegs = 32;
 constexpr int kWdEpiRegs = 112;
 constexpr int kWdMaxDim = 4096;
+constexpr int kWdPushBytes = 8192;      // one bulk copy of the gather pusher (two slots per pusher warp)
 
 struct WdSmem {
   static constexpr int ring = 0;
@@ -67,7 +68,10 @@ struct WdSmem {
   static constexpr int tmem_slot = bars + n_bars * 8;
   static constexpr int units = tmem_slot + 16;
   static constexpr int push_cnt = units + 16;         // int: epilogue warps that have finished a tile (gather pusher)
-  static constexpr int total = push_cnt + 16;
+  // gather pusher, bulk form: per pusher warp two staging slots and their "loaded" mbarriers
+  static constexpr int push_bar = push_cnt + 16;      // [2 warps][2 slots] x 8 bytes
+  static constexpr int push_stage = (push_bar + 32 + 127) & ~127;
+  static constexpr int total = push_stage + 2 * 2 * kWdPushBytes;
 };
 static_assert(WdSmem::total <= 232448, "shared memory budget of one sm_100 CTA exceeded");
 
@@ -96,6 +100,7 @@ struct WdParams {
   // mapping), underneath the CTA's next tile.
   int n_peers;
   int peer_mc;   // 1: peers[0] is an NVLS multicast address (n_peers == 1)
+  int peer_bulk; // 1: the pusher moves the tile with bulk copies (x_out -> shared memory -> every peer) instead of 16-byte stores
   long long peer_off;
   float* peers[kMaxPeers];
 };
@@ -336,6 +341,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     for (int c = 0; c < 8; ++c) mbar_init(wd_bar(smem, WdSmem::a_chunk + c), 4);
     mbar_init(wd_bar(smem, WdSmem::acc_full), 1);
     *reinterpret_cast<volatile int*>(smem + WdSmem::push_cnt) = 0;
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(smem + WdSmem::push_bar + 8 * i), 1);
     fence_mbar_init();
   }
   if (threadIdx.x == 32) mlp_units_compute(P.sched, P.n_steps, reinterpret_cast<volatile MlpUnits*>(smem + WdSmem::units));
@@ -494,6 +500,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
     // 15.8 ms through multicast)
     const int pw = warp - 2;
     const int* cnt_p = reinterpret_cast<const int*>(smem + WdSmem::push_cnt);
+    long long bulk_cnt = 0;   // pieces this warp has moved so far (slot and mbarrier phase of the next one)
     int want = 0;   // a counter, not an mbarrier phase: the pusher may fall more than one tile behind
     for (int tile = units->t_last; tile >= units->t_first; --tile) {
       if (mlp_unit_s1(units, tile, K) != K) continue;   // the burst of this tile ends on another CTA
@@ -512,7 +519,46 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       const float* src = P.x_out + e0;
       bool vec4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (cnt % 4 == 0);
       for (int w = 0; w < P.n_peers; ++w) vec4 = vec4 && ((reinterpret_cast<uintptr_t>(P.peers[w] + P.peer_off + e0) & 15) == 0);
-      if (vec4) {
+      if (vec4 && P.peer_bulk && !P.peer_mc) {
+        // Bulk form: one lane moves the tile in 8 KB pieces, x_out -> staging slot (cp.async.bulk, an L2 hit) -> one bulk
+        // store per peer.  A 16-byte store makes one NVLink request per 16 bytes and lane; a bulk store hands the copy
+        // engine of the SM 8 KB at once.  Two slots per warp: the load of piece i+1 runs under the stores of piece i.
+        if (lane == 0) {
+          const uint32_t stage0 = smem_u32(smem + WdSmem::push_stage + pw * 2 * kWdPushBytes);
+          const uint32_t bar0 = smem_u32(smem + WdSmem::push_bar + 16 * pw);
+          const char* srcb = reinterpret_cast<const char*>(src);
+          const long long bytes = cnt * 4;
+          auto piece = [&](long long i) { return (long long)(pw + 2 * i) * kWdPushBytes; };   // the two warps interleave pieces
+          auto load = [&](long long i) {
+            const long long off = piece(i);
+            const uint32_t sz = (uint32_t)((bytes - off < kWdPushBytes) ? (bytes - off) : kWdPushBytes);
+            const uint32_t slot = (uint32_t)((bulk_cnt + i) & 1);
+            // the slot's previous stores (piece i - 2, committed before piece i - 1 was loaded) must have read it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_expect_tx(bar0 + 8 * slot, sz);
+            bulk_g2s(stage0 + slot * kWdPushBytes, srcb + off, sz, bar0 + 8 * slot);
+          };
+          asm volatile("fence.proxy.async;" ::: "memory");   // the epilogue's generic-proxy stores of the tile -> bulk reads
+          long long n_pieces = 0;
+          while (piece(n_pieces) < bytes) ++n_pieces;
+          if (n_pieces > 0) load(0);
+          for (long long i = 0; i < n_pieces; ++i) {
+            if (i + 1 < n_pieces) load(i + 1);
+            const long long off = piece(i);
+            const uint32_t sz = (uint32_t)((bytes - off < kWdPushBytes) ? (bytes - off) : kWdPushBytes);
+            const uint32_t slot = (uint32_t)((bulk_cnt + i) & 1);
+            mbar_wait(bar0 + 8 * slot, (uint32_t)(((bulk_cnt + i) >> 1) & 1));
+            for (int w = 0; w < P.n_peers; ++w) {
+              char* dst = reinterpret_cast<char*>(P.peers[w] + P.peer_off + e0) + off;
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                           "r"(stage0 + slot * kWdPushBytes), "r"(sz)
+                           : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          bulk_cnt += n_pieces;
+        }
+      } else if (vec4) {
         const long long nv = cnt / 4;
         const float4* s4 = reinterpret_cast<const float4*>(src);
         for (long long i0 = 32 * pw; i0 < nv; i0 += 2 * 64) {       // 2 independent 16-byte loads in flight per lane
@@ -540,6 +586,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
           else for (int w = 0; w < P.n_peers; ++w) P.peers[w][P.peer_off + e0 + i] = v;
         }
       }
+    }
+    if (P.peer_bulk && lane == 0) {   // every bulk store has completed before the CTA (and its staging slots) retire
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __threadfence_system();
     }
   }
   } else {
@@ -963,6 +1013,7 @@ static size_t mlp_wide_weight_bytes(const EbmEnergyDesc* e) {
 }
 size_t mlp_wide_workspace_bytes(const EbmEnergyDesc* e) { return mlp_wide_weight_bytes(e) + kMlpFlagBytes; }
 
+
 bool mlp_wide_supported(const EbmEnergyDesc* e) {
   return e->dim <= kWdMaxDim && e->hidden1 <= kWdH && e->hidden2 <= kWdH;
 }
@@ -1034,6 +1085,7 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     if (c.n_peers > 0 && done + chunk == c.n_steps) {
       P.n_peers = c.n_peers;
       P.peer_mc = c.peer_mc;
+      P.peer_bulk = c.peer_mc ? 0 : wide_push_bulk();
       P.peer_off = c.peer_row_offset * e->dim;
       for (int w = 0; w < c.n_peers; ++w) P.peers[w] = c.peers[w];
     }
