@@ -310,6 +310,48 @@ __device__ __forceinline__ void wd_mma_block(uint32_t tmem_d, uint32_t a_hi, uin
   }
 }
 
+// Gather pusher, bulk form (one lane of a pusher warp; out of line so that its address arithmetic does not take part in
+// the register allocation of the kernel's hot paths): moves the finished tile [src, src + cnt) in 8 KB pieces,
+// x_out -> staging slot (cp.async.bulk, an L2 hit) -> one bulk store per peer.  A 16-byte store makes one NVLink request per
+// 16 bytes and lane; a bulk store hands the SM's copy engine 8 KB at once.  Two slots per warp: the load of piece i+1
+// runs under the stores of piece i.  Returns the warp's running piece count (slot and mbarrier phase of the next piece).
+__device__ __noinline__ long long wd_push_tile_bulk(const WdParams& P, uint8_t* smem, int pw, const float* src, long long e0,
+                                                    long long cnt, long long bulk_cnt) {
+  const uint32_t stage0 = smem_u32(smem + WdSmem::push_stage + pw * 2 * kWdPushBytes);
+  const uint32_t bar0 = smem_u32(smem + WdSmem::push_bar + 16 * pw);
+  const char* srcb = reinterpret_cast<const char*>(src);
+  const long long bytes = cnt * 4;
+  auto piece = [&](long long i) { return (long long)(pw + 2 * i) * kWdPushBytes; };   // the two warps interleave pieces
+  auto load = [&](long long i) {
+    const long long off = piece(i);
+    const uint32_t sz = (uint32_t)((bytes - off < kWdPushBytes) ? (bytes - off) : kWdPushBytes);
+    const uint32_t slot = (uint32_t)((bulk_cnt + i) & 1);
+    // the slot's previous stores (piece i - 2, committed before piece i - 1 was loaded) must have read it
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    mbar_expect_tx(bar0 + 8 * slot, sz);
+    bulk_g2s(stage0 + slot * kWdPushBytes, srcb + off, sz, bar0 + 8 * slot);
+  };
+  asm volatile("fence.proxy.async;" ::: "memory");   // the epilogue's generic-proxy stores of the tile -> bulk reads
+  long long n_pieces = 0;
+  while (piece(n_pieces) < bytes) ++n_pieces;
+  if (n_pieces > 0) load(0);
+  for (long long i = 0; i < n_pieces; ++i) {
+    if (i + 1 < n_pieces) load(i + 1);
+    const long long off = piece(i);
+    const uint32_t sz = (uint32_t)((bytes - off < kWdPushBytes) ? (bytes - off) : kWdPushBytes);
+    const uint32_t slot = (uint32_t)((bulk_cnt + i) & 1);
+    mbar_wait(bar0 + 8 * slot, (uint32_t)(((bulk_cnt + i) >> 1) & 1));
+    for (int w = 0; w < P.n_peers; ++w) {
+      char* dst = reinterpret_cast<char*>(P.peers[w] + P.peer_off + e0) + off;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(stage0 + slot * kWdPushBytes),
+                   "r"(sz)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  return bulk_cnt + n_pieces;
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const __grid_constant__ WdParams P,
                                                                           const __grid_constant__ StepTable tab) {
@@ -520,44 +562,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) langevin_mlp_wide_kernel(const 
       bool vec4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (cnt % 4 == 0);
       for (int w = 0; w < P.n_peers; ++w) vec4 = vec4 && ((reinterpret_cast<uintptr_t>(P.peers[w] + P.peer_off + e0) & 15) == 0);
       if (vec4 && P.peer_bulk && !P.peer_mc) {
-        // Bulk form: one lane moves the tile in 8 KB pieces, x_out -> staging slot (cp.async.bulk, an L2 hit) -> one bulk
-        // store per peer.  A 16-byte store makes one NVLink request per 16 bytes and lane; a bulk store hands the copy
-        // engine of the SM 8 KB at once.  Two slots per warp: the load of piece i+1 runs under the stores of piece i.
-        if (lane == 0) {
-          const uint32_t stage0 = smem_u32(smem + WdSmem::push_stage + pw * 2 * kWdPushBytes);
-          const uint32_t bar0 = smem_u32(smem + WdSmem::push_bar + 16 * pw);
-          const char* srcb = reinterpret_cast<const char*>(src);
-          const long long bytes = cnt * 4;
-          auto piece = [&](long long i) { return (long long)(pw + 2 * i) * kWdPushBytes; };   // the two warps interleave pieces
-          auto load = [&](long long i) {
-            const long long off = piece(i);
-            const uint32_t sz = (uint32_t)((bytes - off < kWdPushBytes) ? (bytes - off) : kWdPushBytes);
-            const uint32_t slot = (uint32_t)((bulk_cnt + i) & 1);
-            // the slot's previous stores (piece i - 2, committed before piece i - 1 was loaded) must have read it
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_expect_tx(bar0 + 8 * slot, sz);
-            bulk_g2s(stage0 + slot * kWdPushBytes, srcb + off, sz, bar0 + 8 * slot);
-          };
-          asm volatile("fence.proxy.async;" ::: "memory");   // the epilogue's generic-proxy stores of the tile -> bulk reads
-          long long n_pieces = 0;
-          while (piece(n_pieces) < bytes) ++n_pieces;
-          if (n_pieces > 0) load(0);
-          for (long long i = 0; i < n_pieces; ++i) {
-            if (i + 1 < n_pieces) load(i + 1);
-            const long long off = piece(i);
-            const uint32_t sz = (uint32_t)((bytes - off < kWdPushBytes) ? (bytes - off) : kWdPushBytes);
-            const uint32_t slot = (uint32_t)((bulk_cnt + i) & 1);
-            mbar_wait(bar0 + 8 * slot, (uint32_t)(((bulk_cnt + i) >> 1) & 1));
-            for (int w = 0; w < P.n_peers; ++w) {
-              char* dst = reinterpret_cast<char*>(P.peers[w] + P.peer_off + e0) + off;
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                           "r"(stage0 + slot * kWdPushBytes), "r"(sz)
-                           : "memory");
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          bulk_cnt += n_pieces;
-        }
+        if (lane == 0) bulk_cnt = wd_push_tile_bulk(P, smem, pw, src, e0, cnt, bulk_cnt);
       } else if (vec4) {
         const long long nv = cnt / 4;
         const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -1095,11 +1100,13 @@ int langevin_mlp_wide_dispatch(const LangevinCall& c, int passes) {
     P.step_base = done;
     int rc0 = mlp_schedule_setup(P.sched, tiles, chunk, grid, flags, c.st);
     if (rc0) return rc0;
+    // the pusher's staging slots are the tail of the layout: only launches with a bulk gather ask for them
+    const int smem_bytes = (P.n_peers > 0 && P.peer_bulk) ? WdSmem::total : WdSmem::push_stage;
 #define CALL(A)                                                                                            \
   {                                                                                                        \
     auto kern = langevin_mlp_wide_kernel<A>;                                                               \
     EBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WdSmem::total));      \
-    EBM_CUDA(mlp_launch_persistent(kern, grid, kWdThreads, WdSmem::total, c.st, P, tab, tiles, chunk, grid)); \
+    EBM_CUDA(mlp_launch_persistent(kern, grid, kWdThreads, smem_bytes, c.st, P, tab, tiles, chunk, grid)); \
   }
     switch (e->activation) {
       case EBM_ACT_SILU: CALL(EBM_ACT_SILU); break;
