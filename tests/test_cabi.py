@@ -47,6 +47,14 @@ def test_abi_version_and_argument_errors_need_no_gpu(lib):
     assert rc == _lib.ERR_INVALID
     with pytest.raises(ValueError):
         _lib.check(rc, "ebm_langevin_burst_f32")
+    # ABI v9: a three-hidden-layer MLP descriptor must carry W3 / b3 in buf[7..8]; the struct layout the header documents
+    assert ctypes.sizeof(_lib.EbmEnergyDesc) == 10 * 4 + 4 * 4 + 10 * 8
+    m = _lib.EbmEnergyDesc()
+    m.kind, m.dim, m.hidden1, m.hidden2, m.hidden3 = _lib.ENERGY_MLP, 8, 8, 8, 8
+    for i in range(6):
+        m.buf[i] = 64   # (never dereferenced: validation fails first)
+    rc = lib.ebm_energy_f32(ctypes.byref(m), ctypes.c_void_p(64), 1, ctypes.c_void_p(64), None)
+    assert rc == _lib.ERR_INVALID and b"W3" in lib.ebm_last_error()
 
 
 def test_missing_library_raises_instead_of_falling_back(monkeypatch, tmp_path):

@@ -125,6 +125,25 @@ def test_energy_descriptor_extraction():
     assert (d.c.hidden1, d.c.hidden2, d.c.activation) == (32, 24, _lib.ACT_TANH)
     assert d.c.buf[0] == mlp.net[0].weight.data_ptr()  # pointers into the live parameters: weights are read fresh
     assert energy_descriptor(mlp, 17, dev) is None
+    assert d.c.hidden3 == 0 and not d.c.buf[7]
+    # three hidden layers (benchmarks/distributed_fsdp2.py:43-53): hidden3 + W3 / b3 in buf[7..8], the output layer stays in buf[4..5]
+    deep = te.MLPEnergy(dim=16, hidden=(32, 24, 40), activation="silu", precision="fp32")
+    d = energy_descriptor(deep, 16, dev)
+    assert (d.c.hidden1, d.c.hidden2, d.c.hidden3) == (32, 24, 40) and d.c.precision == _lib.MLP_BF16X3   # tensor-core kernel only
+    assert d.c.buf[7] == deep.net[4].weight.data_ptr() and d.c.buf[8] == deep.net[4].bias.data_ptr()
+    assert d.c.buf[4] == deep.net[6].weight.data_ptr() and d.c.buf[5] == deep.net[6].bias.data_ptr()
+    assert energy_descriptor(te.MLPEnergy(dim=200, hidden=(32, 24, 40)), 200, dev) is None   # three layers: states up to 128 wide
+    assert energy_descriptor(te.MLPEnergy(dim=16, hidden=(32, 200, 40)), 16, dev) is None
+    with pytest.raises(ValueError):
+        te.MLPEnergy(dim=16, hidden=(32, 24, 40, 8))
+    four = torch.nn.Sequential(*[m for w in ((16, 8), (8, 8), (8, 8), (8, 8)) for m in (torch.nn.Linear(*w), torch.nn.SiLU())],
+                               torch.nn.Linear(8, 1))
+    with pytest.raises(ValueError):
+        te.MLPEnergy(net=four)
+    mixed = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.SiLU(), torch.nn.Linear(8, 8), torch.nn.Tanh(), torch.nn.Linear(8, 8),
+                                torch.nn.SiLU(), torch.nn.Linear(8, 1))
+    with pytest.raises(ValueError):
+        te.MLPEnergy(net=mixed)
 
     class Custom(te.BaseModel):  # user subclass with its own forward: never matched by name
         def forward(self, x):
@@ -159,6 +178,20 @@ def test_mark_mlp_energy_recognises_user_modules():
     assert mark_mlp_energy(m)
     assert energy_descriptor(m, 8, torch.device("cpu")).kind == "mlp"
     assert not mark_mlp_energy(NotAnMLP())
+
+    class DeepUserEBM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 12), torch.nn.Tanh(),
+                                           torch.nn.Linear(12, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+
+        def forward(self, x):
+            return self.net(x).squeeze(-1)
+
+    dm = DeepUserEBM()
+    assert mark_mlp_energy(dm)
+    dd = energy_descriptor(dm, 8, torch.device("cpu"))
+    assert dd.kind == "mlp" and dd.c.hidden3 == 16 and dd.c.activation == _lib.ACT_TANH
 
 
 def test_models_forward_match_oracle_energies():
