@@ -27,6 +27,22 @@ def test_workloads_cover_the_baseline_configs():
                             "c5": (65536, 784, 20)}.items():
         assert b.WORKLOADS[name][1:] == (n, d, k)
     assert "c5" in b.WEAK and b.METRIC == "langevin_chain_steps_per_sec"
+    # the north_star MLP target and its three-hidden-layer sibling: same chains, width and burst length
+    assert b.WORKLOADS["mlp128"][1:] == b.WORKLOADS["mlp128x3"][1:] == (65536, 128, 100)
+
+
+def test_tensor_roofline_counts_every_product_of_the_energy():
+    """4 * (D*H1 + H1*H2 + H2) FLOP per chain-step for two hidden layers; a third adds 4 * H2*H3."""
+    b = _bench()
+    peaks = {"hbm_gbs": 6539.5, "bf16_tflops": 1665.4}
+    units = 65536 * 100
+    two = b.roofline("mlp128", peaks, "measured", 0.0, None, 0, 1.0, units)
+    three = b.roofline("mlp128x3", peaks, "measured", 0.0, None, 0, 1.0, units)
+    assert two["bound"] == three["bound"] == "tensor"
+    assert two["algorithmic_flops_per_launch"] == 4 * (128 * 128 * 2 + 128) * units
+    assert three["algorithmic_flops_per_launch"] == 4 * (128 * 128 * 3 + 128) * units
+    wide = b.roofline("c3", peaks, "measured", 0.0, None, 0, 1.0, 65536 * 20)
+    assert wide["algorithmic_flops_per_launch"] == 4 * (784 * 128 + 128 * 128 + 128) * 65536 * 20
 
 
 def test_measured_peaks_fallback_and_partial_file(tmp_path, monkeypatch):
