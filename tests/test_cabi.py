@@ -73,3 +73,30 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_descriptor_layout_in_python_equals_the_header_compiled_as_c(tmp_path):
+    """include/ebm_b200.h is plain C (no CUDA or torch types): compile a probe with gcc and compare sizeof / offsetof of
+    EbmEnergyDesc and the ABI version with the ctypes mirror every Python call marshals through."""
+    import shutil
+    import subprocess
+
+    from torchebm_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    fields = [f[0] for f in _lib.EbmEnergyDesc._fields_]
+    src = tmp_path / "probe.c"
+    src.write_text(
+        "#include <stddef.h>\n#include <stdio.h>\n#include \"ebm_b200.h\"\nint main(void) {\n"
+        "  printf(\"sizeof %zu\\n\", sizeof(EbmEnergyDesc));\n  printf(\"abi %d\\n\", EBM_ABI_VERSION);\n"
+        + "".join(f"  printf(\"{f} %zu\\n\", offsetof(EbmEnergyDesc, {f}));\n" for f in fields)
+        + "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(_lib.EbmEnergyDesc)
+    assert int(out["abi"]) == _lib.EBM_ABI_VERSION
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.EbmEnergyDesc, f).offset, f
