@@ -160,7 +160,11 @@ int ebm_descent_burst_f32(const EbmEnergyDesc* e, const float* x_in, float* x_ou
  * rank reads its gathered buffer.  Replaces the all_gather of the negatives (utils/distributed.py:43-70).
  * NVLS: pass world = -W and W + 1 pointers, the last one the MULTICAST address of the gathered buffers (symmetric
  * memory's multicast mapping): kernels with a peer-store epilogue then issue ONE multimem.st per 16 bytes, which NVSwitch
- * replicates into all W copies, instead of W stores; the others keep pushing to the W unicast pointers. */
+ * replicates into all W copies, instead of W stores; the others keep pushing to the W unicast pointers.
+ * MLP energies with dim > 128 (the streamed-state kernel): two otherwise idle warps per SM move every finished tile
+ * with 8 KB bulk copies, x_out -> shared memory -> one bulk store per unicast pointer (measured best at 2 and 8 GPUs), and
+ * ignore the multicast pointer; the environment variable EBM_B200_PUSH_BULK=0 selects 16-byte stores instead
+ * (through the multicast address when one was passed). */
 int ebm_langevin_burst_gather_f32(const EbmEnergyDesc* e, const float* x_in, float* x_out, int64_t n, int32_t n_steps,
                                   const double* step_size_host, const double* noise_scale_host, int32_t schedule_len,
                                   const float* clamp_lo_hi_host, int32_t rng_mode, uint64_t seed, uint64_t offset,

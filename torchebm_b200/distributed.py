@@ -90,7 +90,8 @@ class PeerGatherBuffer:
     """The gathered `[n_total, dim]` chain tensor of a sharded burst, allocated in symmetric (peer-mapped) memory so that
     every rank's burst kernel can store its shard straight into every other rank's copy over NVLink
     (`ops.langevin_burst_gather`): the burst-end all-gather without a separate collective launch.  Where the fabric offers
-    NVLS, the kernels store through the buffer's multicast address instead: one store per 16 bytes, replicated by NVSwitch.
+    NVLS, the kernels store through the buffer's multicast address instead: one store per 16 bytes, replicated by NVSwitch
+    (except the streamed-state MLP kernel, whose pusher warps move finished tiles with bulk copies to every peer mapping).
 
     Collective: every rank of `group` must construct it (rendezvous) with the same shape.  `barrier()` is a device-side
     cross-rank barrier on the current stream: call it after the burst before reading `tensor`, and again before the
