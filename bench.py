@@ -886,7 +886,7 @@ def run_reference(args):
         return
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is one CPU job that may use the whole host
     torch.set_num_threads(os.cpu_count() or 1)
-    wl = args.workload if args.workload in ("c1", "c2", "c3", "c5", "mlp128") else "c2"
+    wl = args.workload if args.workload in ("c1", "c2", "c3", "c5", "mlp128", "mlp128x3") else "c2"
     desc_text, n, d, k = WORKLOADS[wl]
     ref = reference_package()
     run, kind, what = _langevin_runner(ref, wl, torch.device("cpu"))
